@@ -1,0 +1,139 @@
+/*
+ * lrfb.h — C ABI of liblrfb.so, the B200 (sm_100a) implementation of the lrf QMF codec hot path.
+ *
+ * The reference (pashtari/lrf) is pure Python: it has no FFI layer for this path, so the drop-in
+ * boundary is the Python function API plus the encoded-bytes layout.  These entry
+ * points are what a binding for that path needs; each one names the reference code it replaces
+ * (paths relative to the reference root).  INTEGRATION.md shows the ctypes stub a maintainer of the
+ * reference would add.
+ *
+ * Conventions: plain pointers and sizes only; `d_` pointers are CUDA device pointers, `h_` pointers
+ * are host pointers; `stream` is a cudaStream_t passed as void* (NULL = default stream); no hidden
+ * allocation on the device-pointer entry points (the caller provides the workspace); every call
+ * returns 0 on success, a negative LRFB_E* code for a bad argument / unsupported shape, or a positive
+ * cudaError_t.  lrfb_last_error() returns a thread-local message for the last failure.
+ * Nothing here has a CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef LRFB_H_
+#define LRFB_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LRFB_ABI_VERSION 1
+
+#define LRFB_E_ARG -1         /* null pointer, non-positive size, bad enum */
+#define LRFB_E_UNSUPPORTED -2 /* shape / rank / bounds outside what the kernels implement */
+#define LRFB_E_WORKSPACE -3   /* workspace too small */
+
+#define LRFB_RGB 0
+#define LRFB_YCBCR 1
+#define LRFB_U8 0
+#define LRFB_F32 1
+
+/* Parameters of lrf.qmf_encode (lrf/compression/qmf.py:116-127) after the host resolved the
+ * rank rule (:215-225, :244-250).  patch=True branches only. */
+typedef struct lrfb_qmf_config {
+  int32_t height, width;    /* image (3, H, W) */
+  int32_t patch_h, patch_w; /* patch_size */
+  int32_t color_space;      /* LRFB_RGB or LRFB_YCBCR */
+  int32_t input_dtype;      /* LRFB_U8 or LRFB_F32 (image.float()) */
+  double scale_h, scale_w;  /* scale_factor of the chroma down-sampling (YCbCr only) */
+  int32_t rank[3];          /* per plane (Y, Cb, Cr) or rank[0] for RGB */
+  float bound_lo, bound_hi; /* bounds */
+  int32_t num_iters;        /* QMF(num_iters=...) */
+} lrfb_qmf_config;
+
+/* Geometry derived from a config: the metadata qmf_encode stores ("original size", "padded size",
+ * "rank", lrf/compression/qmf.py:252-254) and the layout of one image's int8 factor record:
+ *   [U_0 | V_0 | U_1 | V_1 | U_2 | V_2], each factor fiber-major (column r of the (rows x R)
+ *   matrix is contiguous: exactly the bytes encode_matrix zlib-compresses per column,
+ *   lrf/compression/utils.py:368-378). */
+typedef struct lrfb_qmf_layout {
+  int32_t n_planes;
+  int32_t cols; /* N = patch_h*patch_w (YCbCr) or 3*patch_h*patch_w (RGB) */
+  int32_t orig_h[3], orig_w[3], pad_h[3], pad_w[3];
+  int32_t rows[3]; /* M per plane */
+  int32_t rank[3];
+  int64_t u_offset[3], v_offset[3]; /* bytes from the start of the record */
+  int64_t record_bytes;
+  int64_t x_floats; /* f32 elements of all patch matrices of one image */
+} lrfb_qmf_layout;
+
+/* Byte offsets inside the encode workspace (for tests and stage-level callers); plane-major. */
+typedef struct lrfb_qmf_workspace_map {
+  int64_t x[3];     /* f32 [batch][rows][cols] */
+  int64_t u[3];     /* f32 [batch][rows][rank]   init, then final factors */
+  int64_t v[3];     /* f32 [batch][cols][rank] */
+  int64_t gram[3];  /* f64 [batch][cols][cols] */
+  int64_t evec[3];  /* f64 [batch][cols][rank] */
+  int64_t sigma[3]; /* f64 [batch][rank] */
+  int64_t total_bytes;
+} lrfb_qmf_workspace_map;
+
+/* Test hooks for lrfb_qmf_encode (all optional). */
+typedef struct lrfb_qmf_debug {
+  const float* d_init_u[3];     /* inject the SVD init (teacher forcing): [batch][rows][rank] */
+  const float* d_init_v[3];     /* [batch][cols][rank] */
+  const int32_t* d_sign_flip[3]; /* [batch][rank] of +1/-1 applied on top of the sign convention */
+  int32_t stop_after;            /* 0: full encode, 1: after the front end, 2: after the SVD init */
+} lrfb_qmf_debug;
+
+int32_t lrfb_abi_version(void);
+const char* lrfb_last_error(void);
+/* number of CUDA devices visible, or a negative/positive error */
+int32_t lrfb_device_count(void);
+
+int32_t lrfb_qmf_layout_query(const lrfb_qmf_config* cfg, lrfb_qmf_layout* out);
+int32_t lrfb_qmf_workspace_query(const lrfb_qmf_config* cfg, int32_t batch, lrfb_qmf_workspace_map* out);
+
+/* Replaces the body of lrf.qmf_encode between image.float() and the int8 cast
+ * (lrf/compression/qmf.py:227-262): rgb_to_ycbcr, chroma_downsampling(area), pad_image(reflect),
+ * patchify, QMF.decompose (SVDInit + num_iters CoordinateDescent sweeps), .to(int8).
+ * d_images: [batch][3][H][W] of input_dtype; d_factors: [batch][record_bytes] int8. */
+int32_t lrfb_qmf_encode(const lrfb_qmf_config* cfg, int32_t batch, const void* d_images, int8_t* d_factors,
+                        void* d_workspace, int64_t workspace_bytes, const lrfb_qmf_debug* dbg, void* stream);
+
+/* Replaces lrf.qmf_decode after the byte un-packing (lrf/compression/qmf.py:313-351):
+ * QMF.reconstruct, depatchify, unpad_image, chroma_upsampling(nearest), ycbcr_to_rgb, to_dtype(uint8).
+ * d_images: [batch][3][H][W] uint8. */
+int32_t lrfb_qmf_decode(const lrfb_qmf_config* cfg, int32_t batch, const int8_t* d_factors, uint8_t* d_images,
+                        void* stream);
+
+/* Stage-level: only the front end (compression/utils.py:24-47, :76-95, :108-132, compression/qmf.py:43-56).
+ * d_x: f32, plane-major [plane][batch][rows][cols] packed (offsets = workspace map x[] minus x[0]). */
+int32_t lrfb_qmf_frontend(const lrfb_qmf_config* cfg, int32_t batch, const void* d_images, float* d_x,
+                          void* stream);
+
+/* Replaces lrf.QMF(rank, num_iters, bounds).decompose(x) (lrf/factorization/qmf.py:197-214) for a batch of
+ * equally shaped matrices with factor=(0,1): d_x [n_mat][M][N] f32 → d_u [n_mat][M][R], d_v [n_mat][N][R]
+ * (integer-valued f32).  d_init_u/d_init_v optional (skip the SVD init).  Workspace from
+ * lrfb_factorize_workspace_bytes. */
+int64_t lrfb_factorize_workspace_bytes(int32_t n_mat, int32_t M, int32_t N, int32_t R);
+int32_t lrfb_factorize(const float* d_x, int32_t n_mat, int32_t M, int32_t N, int32_t R, float bound_lo,
+                       float bound_hi, int32_t num_iters, float* d_u, float* d_v, const float* d_init_u,
+                       const float* d_init_v, const int32_t* d_sign_flip, void* d_workspace,
+                       int64_t workspace_bytes, void* stream);
+
+/* Exact per-image sum of squared differences of two uint8 batches (lrf/utils/metrics.py:24-35 before
+ * the mean); d_sse [batch] must be zeroed by the caller. psnr = 20*log10(255/sqrt(sse/n)). */
+int32_t lrfb_sse_u8(const uint8_t* d_a, const uint8_t* d_b, int64_t elems_per_image, int32_t batch,
+                    uint64_t* d_sse, void* stream);
+
+/* Host-buffer path (what a CPU caller of lrf.qmf_encode / qmf_decode binds): a context owns a stream
+ * and grow-only device buffers; h_ pointers should be pinned for full copy bandwidth. */
+typedef struct lrfb_ctx lrfb_ctx;
+int32_t lrfb_ctx_create(int32_t device, lrfb_ctx** out);
+void lrfb_ctx_destroy(lrfb_ctx* ctx);
+int32_t lrfb_qmf_encode_host(lrfb_ctx* ctx, const lrfb_qmf_config* cfg, int32_t batch, const void* h_images,
+                             int8_t* h_factors);
+int32_t lrfb_qmf_decode_host(lrfb_ctx* ctx, const lrfb_qmf_config* cfg, int32_t batch, const int8_t* h_factors,
+                             uint8_t* h_images);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LRFB_H_ */

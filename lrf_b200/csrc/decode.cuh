@@ -1,0 +1,106 @@
+// Fused decoder: int8 factors → uint8 RGB image, one thread per output pixel.
+//   QMF.reconstruct (u @ v.mT)   lrf/factorization/qmf.py:216-223   exact small-integer arithmetic
+//   depatchify                   lrf/compression/qmf.py:59-75
+//   unpad_image                  lrf/compression/utils.py:135-153   (start = (Hp-H)//2)
+//   chroma_upsampling (nearest)  lrf/compression/utils.py:98-105    src = min(floorf(dst*in/out), in-1)
+//   ycbcr_to_rgb                 lrf/compression/utils.py:50-73     FMA chain on (ycc + offset)
+//   to_dtype(uint8)              lrf/compression/utils.py:156-182   clamp then truncate
+// HBM-bound: ~0.08 B/pixel of factors in, 3 B/pixel out.  Also the exact per-image SSE used by PSNR
+// (lrf/utils/metrics.py:24-35, :57-71).
+#pragma once
+#include "frontend.cuh"
+
+namespace lrfb {
+
+struct DecodeParams {
+  int H, W, p, q, ycbcr, n_img;
+  PlaneGeom g[3];
+  int rank[3];
+  long long record_bytes;
+  long long u_off[3], v_off[3];
+};
+
+__device__ __forceinline__ unsigned char to_u8_trunc(float v) {
+  v = fminf(fmaxf(v, 0.0f), 255.0f);
+  return (unsigned char)(int)v;
+}
+
+__device__ __forceinline__ float plane_value(const int8_t* __restrict__ rec, const DecodeParams& P, int c,
+                                             int chan, int y, int x) {
+  const PlaneGeom& g = P.g[c];
+  const int yy = y + (g.hp - g.h) / 2, xx = x + (g.wp - g.w) / 2;
+  const int m = (yy / P.p) * g.nbw + xx / P.q;
+  const int col = chan * P.p * P.q + (yy % P.p) * P.q + xx % P.q;
+  const int ncols = P.ycbcr ? P.p * P.q : 3 * P.p * P.q;
+  const int8_t* u = rec + P.u_off[c];
+  const int8_t* v = rec + P.v_off[c];
+  float acc = 0.0f;
+  for (int r = 0; r < P.rank[c]; ++r)
+    acc = __fadd_rn(acc, __fmul_rn((float)u[(size_t)r * g.rows + m], (float)v[(size_t)r * ncols + col]));
+  return acc;
+}
+
+__device__ __forceinline__ int nearest_src(int dst, int in, int out) {
+  if (out == in) return dst;
+  if (out == 2 * in) return dst >> 1;
+  float scale = __fdiv_rn((float)in, (float)out);
+  int s = (int)floorf(__fmul_rn((float)dst, scale));
+  return min(s, in - 1);
+}
+
+__global__ void __launch_bounds__(256)
+qmf_decode_kernel(const int8_t* __restrict__ factors, unsigned char* __restrict__ out, DecodeParams P) {
+  const float t[3][3] = {{1.0f, 0.0f, 1.40200f}, {1.0f, -0.344136f, -0.714136f}, {1.0f, 1.77200f, 0.0f}};
+  const size_t hw = (size_t)P.H * P.W;
+  for (int im = blockIdx.y; im < P.n_img; im += gridDim.y) {
+    const int8_t* rec = factors + (size_t)im * P.record_bytes;
+    unsigned char* o = out + (size_t)im * 3 * hw;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < hw; e += (size_t)gridDim.x * blockDim.x) {
+      const int y = (int)(e / P.W), x = (int)(e - (size_t)y * P.W);
+      if (!P.ycbcr) {
+        for (int c = 0; c < 3; ++c) o[c * hw + e] = to_u8_trunc(plane_value(rec, P, 0, c, y, x));
+        continue;
+      }
+      const int sy = nearest_src(y, P.g[1].h, P.H), sx = nearest_src(x, P.g[1].w, P.W);
+      float ycc[3];
+      ycc[0] = __fadd_rn(plane_value(rec, P, 0, 0, y, x), 0.0f);
+      ycc[1] = __fadd_rn(plane_value(rec, P, 1, 0, sy, sx), -128.0f);
+      ycc[2] = __fadd_rn(plane_value(rec, P, 2, 0, sy, sx), -128.0f);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float acc = __fmul_rn(t[c][0], ycc[0]);
+        acc = __fmaf_rn(t[c][1], ycc[1], acc);
+        acc = __fmaf_rn(t[c][2], ycc[2], acc);
+        o[c * hw + e] = to_u8_trunc(acc);
+      }
+    }
+  }
+}
+
+// exact sum of squared differences per image: integer arithmetic, order-independent
+__global__ void __launch_bounds__(256)
+sse_u8_kernel(const unsigned char* __restrict__ a, const unsigned char* __restrict__ b, long long per_img,
+              int n_img, unsigned long long* __restrict__ sse) {
+  __shared__ unsigned long long warp_sums[8];
+  for (int im = blockIdx.y; im < n_img; im += gridDim.y) {
+    const unsigned char* pa = a + (size_t)im * per_img;
+    const unsigned char* pb = b + (size_t)im * per_img;
+    unsigned long long s = 0;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < per_img;
+         e += (long long)gridDim.x * blockDim.x) {
+      int d = (int)pa[e] - (int)pb[e];
+      s += (unsigned long long)(d * d);
+    }
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long tot = 0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += warp_sums[w];
+      atomicAdd(&sse[im], tot);
+    }
+  }
+}
+
+}  // namespace lrfb

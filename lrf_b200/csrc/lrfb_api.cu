@@ -1,0 +1,568 @@
+// C ABI of liblrfb.so (see include/lrfb.h).  Host-side orchestration of the sm_100a kernels.
+// The same file compiles with g++ -DLRFB_SIM for the test-only CPU SIMT shim (tests/cpu_sim/).
+#include "../../include/lrfb.h"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "bcd.cuh"
+#include "decode.cuh"
+#include "eig.cuh"
+#include "frontend.cuh"
+#include "gram.cuh"
+#include "init.cuh"
+#include "lrfb_common.cuh"
+
+using namespace lrfb;
+
+#define LRFB_EXPORT extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#ifdef LRFB_SIM
+int dev_copy(void* dst, const void* src, size_t n, cudaStream_t) {
+  memcpy(dst, src, n);
+  return 0;
+}
+int check_launch(const char*) { return 0; }
+int num_sms() { return 4; }
+#else
+int dev_copy(void* dst, const void* src, size_t n, cudaStream_t st) {
+  return (int)cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, st);
+}
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail((int)e, "%s: %s", what, cudaGetErrorString(e));
+  return 0;
+}
+int num_sms() {
+  static thread_local int cached = 0;
+  if (!cached) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+    if (cached <= 0) cached = 148;
+  }
+  return cached;
+}
+#endif
+
+inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+struct Geometry {
+  FrontParams fp;
+  lrfb_qmf_layout lay;
+};
+
+int make_geometry(const lrfb_qmf_config* c, int batch, Geometry* g) {
+  if (!c) return fail(LRFB_E_ARG, "config is null");
+  if (c->height <= 0 || c->width <= 0 || c->patch_h <= 0 || c->patch_w <= 0)
+    return fail(LRFB_E_ARG, "non-positive image or patch size");
+  if (c->color_space != LRFB_RGB && c->color_space != LRFB_YCBCR)
+    return fail(LRFB_E_ARG, "color_space must be LRFB_RGB or LRFB_YCBCR");
+  if (c->input_dtype != LRFB_U8 && c->input_dtype != LRFB_F32) return fail(LRFB_E_ARG, "bad input_dtype");
+  const int ycbcr = c->color_space == LRFB_YCBCR;
+  memset(g, 0, sizeof(*g));
+  FrontParams& fp = g->fp;
+  fp.H = c->height, fp.W = c->width, fp.p = c->patch_h, fp.q = c->patch_w, fp.ycbcr = ycbcr, fp.n_img = batch;
+  lrfb_qmf_layout& L = g->lay;
+  L.n_planes = ycbcr ? 3 : 1;
+  L.cols = (ycbcr ? 1 : 3) * c->patch_h * c->patch_w;
+  int64_t off = 0;
+  for (int pl = 0; pl < L.n_planes; ++pl) {
+    int h = c->height, w = c->width;
+    if (ycbcr && pl > 0) {
+      if (!(c->scale_h > 0.0) || !(c->scale_w > 0.0)) return fail(LRFB_E_ARG, "scale_factor must be positive");
+      h = (int)floor((double)c->height * c->scale_h);  // F.interpolate(scale_factor): floor(in*scale)
+      w = (int)floor((double)c->width * c->scale_w);
+      if (h <= 0 || w <= 0) return fail(LRFB_E_UNSUPPORTED, "chroma plane would be empty");
+    }
+    int padh = (c->patch_h - h % c->patch_h) % c->patch_h;  // compression/utils.py:125-130
+    int padw = (c->patch_w - w % c->patch_w) % c->patch_w;
+    PlaneGeom& pg = fp.g[pl];
+    pg.h = h, pg.w = w, pg.hp = h + padh, pg.wp = w + padw, pg.top = padh / 2, pg.left = padw / 2;
+    if (padh - pg.top >= h || padw - pg.left >= w)
+      return fail(LRFB_E_UNSUPPORTED, "reflect padding needs pad < dimension (plane %d is %dx%d)", pl, h, w);
+    pg.nbw = pg.wp / c->patch_w;
+    pg.rows = (pg.hp / c->patch_h) * pg.nbw;
+    L.orig_h[pl] = h, L.orig_w[pl] = w, L.pad_h[pl] = pg.hp, L.pad_w[pl] = pg.wp, L.rows[pl] = pg.rows;
+    L.rank[pl] = c->rank[pl];
+    if (c->rank[pl] <= 0) return fail(LRFB_E_ARG, "rank[%d] must be positive", pl);
+    if (c->rank[pl] > kGenMaxR) return fail(LRFB_E_UNSUPPORTED, "rank %d > %d", c->rank[pl], kGenMaxR);
+    L.u_offset[pl] = off;
+    off += (int64_t)pg.rows * c->rank[pl];
+    L.v_offset[pl] = off;
+    off += (int64_t)L.cols * c->rank[pl];
+    L.x_floats += (int64_t)pg.rows * L.cols;
+  }
+  L.record_bytes = off;
+  if (L.cols > 1024) return fail(LRFB_E_UNSUPPORTED, "patch too large (N=%d)", L.cols);
+  return 0;
+}
+
+int check_bounds(float lo, float hi) {
+  if (!(ceilf(lo) <= floorf(hi))) return fail(LRFB_E_ARG, "empty bounds");
+  if (ceilf(lo) < -128.0f || floorf(hi) > 127.0f)
+    return fail(LRFB_E_UNSUPPORTED, "bounds outside int8 are not implemented");
+  return 0;
+}
+
+int make_map(const Geometry& g, int batch, lrfb_qmf_workspace_map* m) {
+  memset(m, 0, sizeof(*m));
+  int64_t off = 0;
+  const lrfb_qmf_layout& L = g.lay;
+  for (int pl = 0; pl < L.n_planes; ++pl) {
+    m->x[pl] = off;
+    off = align_up(off + (int64_t)batch * L.rows[pl] * L.cols * 4, 256);
+  }
+  for (int pl = 0; pl < L.n_planes; ++pl) {
+    m->u[pl] = off;
+    off = align_up(off + (int64_t)batch * L.rows[pl] * L.rank[pl] * 4, 256);
+    m->v[pl] = off;
+    off = align_up(off + (int64_t)batch * L.cols * L.rank[pl] * 4, 256);
+    m->gram[pl] = off;
+    off = align_up(off + (int64_t)batch * L.cols * L.cols * 8, 256);
+    m->evec[pl] = off;
+    off = align_up(off + (int64_t)batch * L.cols * L.rank[pl] * 8, 256);
+    m->sigma[pl] = off;
+    off = align_up(off + (int64_t)batch * L.rank[pl] * 8, 256);
+  }
+  m->total_bytes = off;
+  return 0;
+}
+
+// ---- factorisation of one batch of equally shaped matrices ------------------------------------------
+struct FactorWs {  // scratch beyond x/u/v/gram/evec/sigma
+  static int gram_split(int n_mat, int M) {
+    int tiles = (M + kGramTileRows - 1) / kGramTileRows;
+    int want = (2 * num_sms() + n_mat - 1) / n_mat;
+    return std::max(1, std::min(std::min(want, tiles), 32));
+  }
+  static int64_t bytes(int n_mat, int M, int N, int R) {
+    int split = gram_split(n_mat, M);
+    int64_t b = 0;
+    if (split > 1) b += align_up((int64_t)n_mat * split * N * N * 8, 256);
+    b += align_up((int64_t)n_mat * (int64_t)EigScratch::doubles(N, R) * 8, 256);
+    b += align_up((int64_t)4096 * 2 * R * R * 4, 256);  // bcd_generic bwork
+    return b;
+  }
+};
+
+template <int BPT>
+void launch_gram(const float* x, long long xs, int M, int N, double* out, int split, int n_mat, int threads,
+                 cudaStream_t st) {
+  size_t smem = (size_t)kGramTileRows * ((N + 3) & ~3) * 8;
+  LRFB_LAUNCH(gram_kernel<BPT>, dim3(split, n_mat), dim3(threads), smem, st, x, xs, M, N, out, split);
+}
+
+template <int R>
+int launch_bcd_fast(const BcdBatch& b, cudaStream_t st) {
+  constexpr int N = 64, TM = 128, NT = 64;
+  auto kern = bcd_kernel<N, R, TM, NT>;
+  size_t smem = sizeof(BcdSmem<N, R, TM, NT>);
+  int per_sm = 2;
+#ifndef LRFB_SIM
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail((int)e, "bcd smem attribute: %s", cudaGetErrorString(e));
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem);
+  if (per_sm < 1) per_sm = 1;
+#endif
+  int grid = std::min(b.n_mat, num_sms() * per_sm);
+  LRFB_LAUNCH(kern, dim3(grid), dim3(NT), smem, st, b);
+  return check_launch("bcd_kernel");
+}
+
+int run_bcd(const BcdBatch& b, int N, int R, float* bwork, cudaStream_t st) {
+  const bool fast = (N == 64 && R <= 4 && !bmm_native(N, b.M, R));
+  if (fast) {
+    switch (R) {
+      case 1: return launch_bcd_fast<1>(b, st);
+      case 2: return launch_bcd_fast<2>(b, st);
+      case 3: return launch_bcd_fast<3>(b, st);
+      default: return launch_bcd_fast<4>(b, st);
+    }
+  }
+  int grid = std::min(b.n_mat, 4096);
+  LRFB_LAUNCH(bcd_generic_kernel, dim3(grid), dim3(256), 0, st, b, N, R, bwork);
+  return check_launch("bcd_generic_kernel");
+}
+
+// SVD init (unless injected) + sweeps.  u, v: f32 working/output buffers.
+int factorize_batch(const float* x, int n_mat, int M, int N, int R, float lo, float hi, int iters, float* u,
+                    float* v, int8_t* uq, int8_t* vq, long long q_stride, const float* init_u,
+                    const float* init_v, const int32_t* sign_flip, double* gram, double* evec, double* sigma,
+                    unsigned char* scratch, int stop_after_init, cudaStream_t st) {
+  int rc;
+  const int split = FactorWs::gram_split(n_mat, M);
+  double* gram_part = nullptr;
+  if (split > 1) {
+    gram_part = reinterpret_cast<double*>(scratch);
+    scratch += align_up((int64_t)n_mat * split * N * N * 8, 256);
+  }
+  double* eig_scratch = reinterpret_cast<double*>(scratch);
+  scratch += align_up((int64_t)n_mat * (int64_t)EigScratch::doubles(N, R) * 8, 256);
+  float* bwork = reinterpret_cast<float*>(scratch);
+
+  if (init_u && init_v) {
+    if ((rc = dev_copy(u, init_u, (size_t)n_mat * M * R * 4, st))) return fail(rc, "copy init u");
+    if ((rc = dev_copy(v, init_v, (size_t)n_mat * N * R * 4, st))) return fail(rc, "copy init v");
+  } else {
+    // G = X^T X in f64
+    const int nb = ((N + 3) / 4);
+    const int nblocks = nb * (nb + 1) / 2;
+    double* gout = split > 1 ? gram_part : gram;
+    for (int m0 = 0; m0 < n_mat; m0 += 65535) {
+      int cnt = std::min(65535, n_mat - m0);
+      const float* xx = x + (size_t)m0 * M * N;
+      double* go = gout + (size_t)m0 * split * N * N;
+      if (nblocks <= 160) {
+        launch_gram<1>(xx, (long long)M * N, M, N, go, split, cnt, ((nblocks + 31) / 32) * 32, st);
+      } else {
+        int threads = std::min(512, (((nblocks + 4) / 5 + 31) / 32) * 32);
+        if ((long long)threads * 5 < nblocks) return fail(LRFB_E_UNSUPPORTED, "N=%d too large for gram", N);
+        launch_gram<5>(xx, (long long)M * N, M, N, go, split, cnt, threads, st);
+      }
+      if ((rc = check_launch("gram_kernel"))) return rc;
+      if (split > 1) {
+        LRFB_LAUNCH(gram_reduce_kernel, dim3((N * N + 255) / 256, cnt), dim3(256), 0, st, go,
+                    gram + (size_t)m0 * N * N, N * N, split);
+        if ((rc = check_launch("gram_reduce_kernel"))) return rc;
+      }
+    }
+    // top-R eigenpairs
+    const int use_shared = N <= 64;
+    const int threads = std::max(64, std::min(256, ((N + 31) / 32) * 32));
+    LRFB_LAUNCH(eig_topr_kernel, dim3(n_mat), dim3(threads), use_shared ? (size_t)N * N * 8 : 0, st, gram, N, R,
+                eig_scratch, evec, sigma, sign_flip, use_shared);
+    if ((rc = check_launch("eig_topr_kernel"))) return rc;
+    // u0, v0
+    for (int m0 = 0; m0 < n_mat; m0 += 65535) {
+      int cnt = std::min(65535, n_mat - m0);
+      int gx = std::max(1, std::min((M + 127) / 128, 64));
+      LRFB_LAUNCH(svd_project_kernel, dim3(gx, cnt), dim3(128), (size_t)N * R * 8, st, x + (size_t)m0 * M * N,
+                  (long long)M * N, M, N, R, evec + (size_t)m0 * N * R, sigma + (size_t)m0 * R,
+                  u + (size_t)m0 * M * R, v + (size_t)m0 * N * R);
+      if ((rc = check_launch("svd_project_kernel"))) return rc;
+    }
+  }
+  if (stop_after_init) return 0;
+  BcdBatch b;
+  b.X = x, b.x_stride = (long long)M * N, b.U = u, b.V = v, b.Uq = uq, b.Vq = vq;
+  b.uq_stride = b.vq_stride = q_stride;
+  b.M = M, b.n_mat = n_mat, b.num_iters = iters, b.lo = ceilf(lo), b.hi = floorf(hi);
+  if (iters <= 0) return fail(LRFB_E_UNSUPPORTED, "num_iters must be >= 1");
+  return run_bcd(b, N, R, bwork, st);
+}
+
+int64_t encode_scratch_bytes(const Geometry& g, int batch) {
+  int64_t mx = 0;
+  for (int pl = 0; pl < g.lay.n_planes; ++pl)
+    mx = std::max(mx, FactorWs::bytes(batch, g.lay.rows[pl], g.lay.cols, g.lay.rank[pl]));
+  return mx;
+}
+
+int run_frontend(const lrfb_qmf_config* cfg, const Geometry& g, int batch, const void* d_images,
+                 float* const* xs, cudaStream_t st) {
+  for (int pl = 0; pl < g.lay.n_planes; ++pl) {
+    long long per_img = (long long)g.lay.rows[pl] * g.lay.cols;
+    int gx = (int)std::min<long long>((per_img + 255) / 256, 8192);
+    dim3 grid(gx, std::min(batch, 65535));
+    if (cfg->input_dtype == LRFB_U8)
+      LRFB_LAUNCH(frontend_kernel<unsigned char>, grid, dim3(256), 0, st, (const unsigned char*)d_images,
+                  xs[pl], g.fp, pl);
+    else
+      LRFB_LAUNCH(frontend_kernel<float>, grid, dim3(256), 0, st, (const float*)d_images, xs[pl], g.fp, pl);
+    int rc = check_launch("frontend_kernel");
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+}  // namespace
+
+// =====================================================================================================
+
+LRFB_EXPORT int32_t lrfb_abi_version(void) { return LRFB_ABI_VERSION; }
+LRFB_EXPORT const char* lrfb_last_error(void) { return g_err; }
+
+LRFB_EXPORT int32_t lrfb_device_count(void) {
+#ifdef LRFB_SIM
+  return 0;
+#else
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) return fail((int)e, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+  return n;
+#endif
+}
+
+LRFB_EXPORT int32_t lrfb_qmf_layout_query(const lrfb_qmf_config* cfg, lrfb_qmf_layout* out) {
+  if (!out) return fail(LRFB_E_ARG, "out is null");
+  Geometry g;
+  int rc = make_geometry(cfg, 1, &g);
+  if (rc) return rc;
+  *out = g.lay;
+  return 0;
+}
+
+LRFB_EXPORT int32_t lrfb_qmf_workspace_query(const lrfb_qmf_config* cfg, int32_t batch,
+                                             lrfb_qmf_workspace_map* out) {
+  if (!out || batch <= 0) return fail(LRFB_E_ARG, "bad arguments");
+  Geometry g;
+  int rc = make_geometry(cfg, batch, &g);
+  if (rc) return rc;
+  make_map(g, batch, out);
+  out->total_bytes += encode_scratch_bytes(g, batch);
+  return 0;
+}
+
+LRFB_EXPORT int32_t lrfb_qmf_frontend(const lrfb_qmf_config* cfg, int32_t batch, const void* d_images,
+                                      float* d_x, void* stream) {
+  if (!d_images || !d_x || batch <= 0) return fail(LRFB_E_ARG, "bad arguments");
+  Geometry g;
+  int rc = make_geometry(cfg, batch, &g);
+  if (rc) return rc;
+  lrfb_qmf_workspace_map m;
+  make_map(g, batch, &m);
+  float* xs[3] = {nullptr, nullptr, nullptr};
+  for (int pl = 0; pl < g.lay.n_planes; ++pl)
+    xs[pl] = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(d_x) + (m.x[pl] - m.x[0]));
+  return run_frontend(cfg, g, batch, d_images, xs, (cudaStream_t)(uintptr_t)stream);
+}
+
+LRFB_EXPORT int32_t lrfb_qmf_encode(const lrfb_qmf_config* cfg, int32_t batch, const void* d_images,
+                                    int8_t* d_factors, void* d_workspace, int64_t workspace_bytes,
+                                    const lrfb_qmf_debug* dbg, void* stream) {
+  if (!d_images || !d_factors || !d_workspace || batch <= 0) return fail(LRFB_E_ARG, "bad arguments");
+  Geometry g;
+  int rc = make_geometry(cfg, batch, &g);
+  if (rc) return rc;
+  if ((rc = check_bounds(cfg->bound_lo, cfg->bound_hi))) return rc;
+  lrfb_qmf_workspace_map m;
+  make_map(g, batch, &m);
+  const int64_t need = m.total_bytes + encode_scratch_bytes(g, batch);
+  if (workspace_bytes < need)
+    return fail(LRFB_E_WORKSPACE, "workspace %lld < required %lld bytes", (long long)workspace_bytes, (long long)need);
+  cudaStream_t st = (cudaStream_t)(uintptr_t)stream;
+  unsigned char* ws = reinterpret_cast<unsigned char*>(d_workspace);
+  float* xs[3];
+  for (int pl = 0; pl < 3; ++pl) xs[pl] = reinterpret_cast<float*>(ws + m.x[pl]);
+  if ((rc = run_frontend(cfg, g, batch, d_images, xs, st))) return rc;
+  if (dbg && dbg->stop_after == 1) return 0;
+  const lrfb_qmf_layout& L = g.lay;
+  for (int pl = 0; pl < L.n_planes; ++pl) {
+    rc = factorize_batch(xs[pl], batch, L.rows[pl], L.cols, L.rank[pl], cfg->bound_lo, cfg->bound_hi,
+                         cfg->num_iters, reinterpret_cast<float*>(ws + m.u[pl]),
+                         reinterpret_cast<float*>(ws + m.v[pl]), d_factors + L.u_offset[pl],
+                         d_factors + L.v_offset[pl], L.record_bytes, dbg ? dbg->d_init_u[pl] : nullptr,
+                         dbg ? dbg->d_init_v[pl] : nullptr, dbg ? dbg->d_sign_flip[pl] : nullptr,
+                         reinterpret_cast<double*>(ws + m.gram[pl]), reinterpret_cast<double*>(ws + m.evec[pl]),
+                         reinterpret_cast<double*>(ws + m.sigma[pl]), ws + m.total_bytes,
+                         dbg && dbg->stop_after == 2, st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+LRFB_EXPORT int64_t lrfb_factorize_workspace_bytes(int32_t n_mat, int32_t M, int32_t N, int32_t R) {
+  if (n_mat <= 0 || M <= 0 || N <= 0 || R <= 0) return 0;
+  return align_up((int64_t)n_mat * N * N * 8, 256) + align_up((int64_t)n_mat * N * R * 8, 256) +
+         align_up((int64_t)n_mat * R * 8, 256) + FactorWs::bytes(n_mat, M, N, R);
+}
+
+LRFB_EXPORT int32_t lrfb_factorize(const float* d_x, int32_t n_mat, int32_t M, int32_t N, int32_t R,
+                                   float bound_lo, float bound_hi, int32_t num_iters, float* d_u, float* d_v,
+                                   const float* d_init_u, const float* d_init_v, const int32_t* d_sign_flip,
+                                   void* d_workspace, int64_t workspace_bytes, void* stream) {
+  if (!d_x || !d_u || !d_v || !d_workspace || n_mat <= 0 || M <= 0 || N <= 0 || R <= 0)
+    return fail(LRFB_E_ARG, "bad arguments");
+  if (R > kGenMaxR || N > 1024) return fail(LRFB_E_UNSUPPORTED, "N=%d R=%d not implemented", N, R);
+  int rc = check_bounds(bound_lo, bound_hi);
+  if (rc) return rc;
+  if (workspace_bytes < lrfb_factorize_workspace_bytes(n_mat, M, N, R))
+    return fail(LRFB_E_WORKSPACE, "workspace too small");
+  unsigned char* ws = reinterpret_cast<unsigned char*>(d_workspace);
+  double* gram = reinterpret_cast<double*>(ws);
+  ws += align_up((int64_t)n_mat * N * N * 8, 256);
+  double* evec = reinterpret_cast<double*>(ws);
+  ws += align_up((int64_t)n_mat * N * R * 8, 256);
+  double* sigma = reinterpret_cast<double*>(ws);
+  ws += align_up((int64_t)n_mat * R * 8, 256);
+  return factorize_batch(d_x, n_mat, M, N, R, bound_lo, bound_hi, num_iters, d_u, d_v, nullptr, nullptr, 0,
+                         d_init_u, d_init_v, d_sign_flip, gram, evec, sigma, ws, 0,
+                         (cudaStream_t)(uintptr_t)stream);
+}
+
+LRFB_EXPORT int32_t lrfb_qmf_decode(const lrfb_qmf_config* cfg, int32_t batch, const int8_t* d_factors,
+                                    uint8_t* d_images, void* stream) {
+  if (!d_factors || !d_images || batch <= 0) return fail(LRFB_E_ARG, "bad arguments");
+  Geometry g;
+  int rc = make_geometry(cfg, batch, &g);
+  if (rc) return rc;
+  DecodeParams P;
+  memset(&P, 0, sizeof(P));
+  P.H = cfg->height, P.W = cfg->width, P.p = cfg->patch_h, P.q = cfg->patch_w;
+  P.ycbcr = cfg->color_space == LRFB_YCBCR, P.n_img = batch, P.record_bytes = g.lay.record_bytes;
+  for (int pl = 0; pl < 3; ++pl) {
+    P.g[pl] = g.fp.g[pl], P.rank[pl] = g.lay.rank[pl];
+    P.u_off[pl] = g.lay.u_offset[pl], P.v_off[pl] = g.lay.v_offset[pl];
+  }
+  long long hw = (long long)cfg->height * cfg->width;
+  dim3 grid((unsigned)std::min<long long>((hw + 255) / 256, 8192), std::min(batch, 65535));
+  LRFB_LAUNCH(qmf_decode_kernel, grid, dim3(256), 0, (cudaStream_t)(uintptr_t)stream, d_factors, d_images, P);
+  return check_launch("qmf_decode_kernel");
+}
+
+LRFB_EXPORT int32_t lrfb_sse_u8(const uint8_t* d_a, const uint8_t* d_b, int64_t elems_per_image, int32_t batch,
+                                uint64_t* d_sse, void* stream) {
+  if (!d_a || !d_b || !d_sse || batch <= 0 || elems_per_image <= 0) return fail(LRFB_E_ARG, "bad arguments");
+  dim3 grid((unsigned)std::min<long long>((elems_per_image + 256 * 16 - 1) / (256 * 16), 1024),
+            std::min(batch, 65535));
+  LRFB_LAUNCH(sse_u8_kernel, grid, dim3(256), 0, (cudaStream_t)(uintptr_t)stream, d_a, d_b,
+              (long long)elems_per_image, batch, reinterpret_cast<unsigned long long*>(d_sse));
+  return check_launch("sse_u8_kernel");
+}
+
+// ---- host-buffer path ----------------------------------------------------------------------------
+
+struct lrfb_ctx {
+  int device;
+  cudaStream_t stream;
+  void* d_in;
+  void* d_out;
+  void* d_ws;
+  size_t in_cap, out_cap, ws_cap;
+};
+
+#ifdef LRFB_SIM
+namespace {
+int grow(void** p, size_t* cap, size_t need) {
+  if (*cap >= need) return 0;
+  free(*p);
+  *p = malloc(need);
+  *cap = need;
+  return *p ? 0 : fail(2, "out of memory");
+}
+int h2d(void* d, const void* h, size_t n, cudaStream_t) { memcpy(d, h, n); return 0; }
+int d2h(void* h, const void* d, size_t n, cudaStream_t) { memcpy(h, d, n); return 0; }
+int sync_stream(cudaStream_t) { return 0; }
+}  // namespace
+LRFB_EXPORT int32_t lrfb_ctx_create(int32_t device, lrfb_ctx** out) {
+  if (!out) return fail(LRFB_E_ARG, "out is null");
+  *out = new lrfb_ctx();
+  memset(*out, 0, sizeof(lrfb_ctx));
+  (*out)->device = device;
+  return 0;
+}
+LRFB_EXPORT void lrfb_ctx_destroy(lrfb_ctx* c) {
+  if (!c) return;
+  free(c->d_in), free(c->d_out), free(c->d_ws);
+  delete c;
+}
+#else
+namespace {
+int grow(void** p, size_t* cap, size_t need) {
+  if (*cap >= need) return 0;
+  if (*p) cudaFree(*p);
+  *p = nullptr, *cap = 0;
+  cudaError_t e = cudaMalloc(p, need);
+  if (e != cudaSuccess) return fail((int)e, "cudaMalloc(%zu): %s", need, cudaGetErrorString(e));
+  *cap = need;
+  return 0;
+}
+int h2d(void* d, const void* h, size_t n, cudaStream_t st) {
+  cudaError_t e = cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, st);
+  return e == cudaSuccess ? 0 : fail((int)e, "H2D: %s", cudaGetErrorString(e));
+}
+int d2h(void* h, const void* d, size_t n, cudaStream_t st) {
+  cudaError_t e = cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, st);
+  return e == cudaSuccess ? 0 : fail((int)e, "D2H: %s", cudaGetErrorString(e));
+}
+int sync_stream(cudaStream_t st) {
+  cudaError_t e = cudaStreamSynchronize(st);
+  return e == cudaSuccess ? 0 : fail((int)e, "stream sync: %s", cudaGetErrorString(e));
+}
+}  // namespace
+LRFB_EXPORT int32_t lrfb_ctx_create(int32_t device, lrfb_ctx** out) {
+  if (!out) return fail(LRFB_E_ARG, "out is null");
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return fail((int)e, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+  lrfb_ctx* c = new lrfb_ctx();
+  memset(c, 0, sizeof(*c));
+  c->device = device;
+  e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete c;
+    return fail((int)e, "cudaStreamCreate: %s", cudaGetErrorString(e));
+  }
+  *out = c;
+  return 0;
+}
+LRFB_EXPORT void lrfb_ctx_destroy(lrfb_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->d_in) cudaFree(c->d_in);
+  if (c->d_out) cudaFree(c->d_out);
+  if (c->d_ws) cudaFree(c->d_ws);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+#endif
+
+LRFB_EXPORT int32_t lrfb_qmf_encode_host(lrfb_ctx* c, const lrfb_qmf_config* cfg, int32_t batch,
+                                         const void* h_images, int8_t* h_factors) {
+  if (!c || !h_images || !h_factors || batch <= 0) return fail(LRFB_E_ARG, "bad arguments");
+  lrfb_qmf_workspace_map m;
+  lrfb_qmf_layout L;
+  int rc;
+  if ((rc = lrfb_qmf_layout_query(cfg, &L))) return rc;
+  if ((rc = lrfb_qmf_workspace_query(cfg, batch, &m))) return rc;
+#ifndef LRFB_SIM
+  cudaSetDevice(c->device);
+#endif
+  size_t in_bytes = (size_t)batch * 3 * cfg->height * cfg->width * (cfg->input_dtype == LRFB_U8 ? 1 : 4);
+  size_t out_bytes = (size_t)batch * L.record_bytes;
+  if ((rc = grow(&c->d_in, &c->in_cap, in_bytes))) return rc;
+  if ((rc = grow(&c->d_out, &c->out_cap, out_bytes))) return rc;
+  if ((rc = grow(&c->d_ws, &c->ws_cap, (size_t)m.total_bytes))) return rc;
+  if ((rc = h2d(c->d_in, h_images, in_bytes, c->stream))) return rc;
+  if ((rc = lrfb_qmf_encode(cfg, batch, c->d_in, (int8_t*)c->d_out, c->d_ws, m.total_bytes, nullptr,
+                            (void*)(uintptr_t)c->stream)))
+    return rc;
+  if ((rc = d2h(h_factors, c->d_out, out_bytes, c->stream))) return rc;
+  return sync_stream(c->stream);
+}
+
+LRFB_EXPORT int32_t lrfb_qmf_decode_host(lrfb_ctx* c, const lrfb_qmf_config* cfg, int32_t batch,
+                                         const int8_t* h_factors, uint8_t* h_images) {
+  if (!c || !h_images || !h_factors || batch <= 0) return fail(LRFB_E_ARG, "bad arguments");
+  lrfb_qmf_layout L;
+  int rc;
+  if ((rc = lrfb_qmf_layout_query(cfg, &L))) return rc;
+#ifndef LRFB_SIM
+  cudaSetDevice(c->device);
+#endif
+  size_t img_bytes = (size_t)batch * 3 * cfg->height * cfg->width;
+  size_t fac_bytes = (size_t)batch * L.record_bytes;
+  if ((rc = grow(&c->d_in, &c->in_cap, fac_bytes))) return rc;
+  if ((rc = grow(&c->d_out, &c->out_cap, img_bytes))) return rc;
+  if ((rc = h2d(c->d_in, h_factors, fac_bytes, c->stream))) return rc;
+  if ((rc = lrfb_qmf_decode(cfg, batch, (const int8_t*)c->d_in, (uint8_t*)c->d_out, (void*)(uintptr_t)c->stream)))
+    return rc;
+  if ((rc = d2h(h_images, c->d_out, img_bytes, c->stream))) return rc;
+  return sync_stream(c->stream);
+}
