@@ -1,0 +1,275 @@
+"""Host-side mirror of the reference codec interface for the QMF hot path.
+
+Same names, argument meaning, error behaviour and encoded-bytes layout as
+``lrf.qmf_encode`` / ``lrf.qmf_decode`` (lrf/compression/qmf.py:116-353), so either decoder reads
+either encoder's output.  The arithmetic between ``image.float()`` and the int8 factors — and between
+the int8 factors and the uint8 image — runs in the sm_100a kernels behind ``liblrfb.so``; there is no
+CPU fallback.  Lossless byte packing (zlib) stays on the host (lrf_b200/packing.py).
+
+The reference has no batch API; ``qmf_encode_batch`` / ``qmf_decode_batch`` add one (single image =
+batch of one).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from collections.abc import Iterable
+from concurrent.futures import ThreadPoolExecutor
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _cabi, packing
+
+_POOL: Optional[ThreadPoolExecutor] = None
+
+
+def _pool() -> ThreadPoolExecutor:
+    global _POOL
+    if _POOL is None:
+        import os
+
+        _POOL = ThreadPoolExecutor(max_workers=max(1, os.cpu_count() or 1))
+    return _POOL
+
+
+def _require_cuda() -> None:
+    if not torch.cuda.is_available():
+        raise _cabi.LrfbError("lrf_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+
+
+def _stream_ptr() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def qmf_rank(size: tuple[int, int], com_ratio: float) -> int:
+    """lrf/compression/qmf.py:25-40."""
+    num_rows, num_cols = size
+    return max(math.floor(num_rows * num_cols / (com_ratio * (num_rows + num_cols))), 1)
+
+
+def _triple(value, halve):
+    if isinstance(value, Iterable):
+        return tuple(value)
+    if value is None:
+        return (None, None, None)
+    return (value, halve(value), halve(value))
+
+
+def resolve_plan(height, width, rank, quality, color_space, scale_factor, patch_size, bounds, num_iters,
+                 input_dtype=_cabi.LRFB_U8):
+    """Apply the reference's rank rule (compression/qmf.py:215-225, :244-250) → (config, layout)."""
+    probe = _cabi.make_config(height, width, patch_size, color_space, input_dtype, scale_factor, (1, 1, 1),
+                              bounds, num_iters)
+    lay = _cabi.QmfLayout()
+    _cabi.check(_cabi.lib().lrfb_qmf_layout_query(C.byref(probe), C.byref(lay)), "lrfb_qmf_layout_query")
+    if color_space == "RGB":
+        if rank is None:
+            assert quality >= 0 and quality <= 100, "'quality' must be between 0 and 100."
+            ranks = [max(round(min(lay.rows[0], lay.cols) * quality / 100), 1)]
+        else:
+            ranks = [rank]
+    else:
+        rk = _triple(rank, lambda r: max(r // 2, 1))
+        ql = _triple(quality, lambda q: q / 2)
+        ranks = []
+        for i in range(3):
+            if rk[i] is None:
+                assert ql[i] >= 0 and ql[i] <= 100, "'quality' must be between 0 and 100."
+                ranks.append(max(round(min(lay.rows[i], lay.cols) * ql[i] / 100), 1))
+            else:
+                ranks.append(rk[i])
+    cfg = _cabi.make_config(height, width, patch_size, color_space, input_dtype, scale_factor, ranks, bounds,
+                            num_iters)
+    _cabi.check(_cabi.lib().lrfb_qmf_layout_query(C.byref(cfg), C.byref(lay)), "lrfb_qmf_layout_query")
+    return cfg, lay
+
+
+def _metadata(image_dtype, color_space, patch, bounds, patch_size, lay) -> dict:
+    """The JSON header, key order as the reference inserts them (compression/qmf.py:157-162, :180-187,
+    :233-254)."""
+    meta = {"dtype": str(image_dtype).split(".")[-1], "color space": color_space, "patch": patch,
+            "bounds": bounds}
+    if color_space == "RGB":
+        meta.update({"patch size": patch_size, "original size": [lay.orig_h[0], lay.orig_w[0]],
+                     "padded size": [lay.pad_h[0], lay.pad_w[0]], "rank": lay.rank[0]})
+    else:
+        meta["patch size"] = patch_size
+        meta["original size"] = [[lay.orig_h[i], lay.orig_w[i]] for i in range(3)]
+        meta["padded size"] = [[lay.pad_h[i], lay.pad_w[i]] for i in range(3)]
+        meta["rank"] = [lay.rank[i] for i in range(3)]
+    return meta
+
+
+class EncodePlan:
+    """Resolved configuration + device buffers for a fixed (shape, batch); reusable across calls."""
+
+    def __init__(self, cfg, lay, batch: int, device):
+        self.cfg, self.lay, self.batch, self.device = cfg, lay, batch, device
+        m = _cabi.QmfWorkspaceMap()
+        _cabi.check(_cabi.lib().lrfb_qmf_workspace_query(C.byref(cfg), batch, C.byref(m)),
+                    "lrfb_qmf_workspace_query")
+        self.map = m
+        self.workspace = torch.empty(m.total_bytes, dtype=torch.uint8, device=device)
+        self.factors = torch.empty((batch, lay.record_bytes), dtype=torch.int8, device=device)
+
+    def run(self, images: torch.Tensor, debug: Optional[_cabi.QmfDebug] = None) -> torch.Tensor:
+        """images: (batch,3,H,W) contiguous on self.device, uint8 or float32 → int8 records on device."""
+        assert images.is_cuda and images.is_contiguous() and images.shape[0] == self.batch
+        rc = _cabi.lib().lrfb_qmf_encode(
+            C.byref(self.cfg), self.batch, C.c_void_p(images.data_ptr()), C.c_void_p(self.factors.data_ptr()),
+            C.c_void_p(self.workspace.data_ptr()), self.map.total_bytes,
+            C.byref(debug) if debug is not None else None, _stream_ptr())
+        _cabi.check(rc, "lrfb_qmf_encode")
+        return self.factors
+
+    def view(self, name: str, plane: int) -> torch.Tensor:
+        """A typed view into the workspace (tests / stage-level inspection)."""
+        lay, b = self.lay, self.batch
+        shapes = {
+            "x": (torch.float32, (b, lay.rows[plane], lay.cols)),
+            "u": (torch.float32, (b, lay.rows[plane], lay.rank[plane])),
+            "v": (torch.float32, (b, lay.cols, lay.rank[plane])),
+            "gram": (torch.float64, (b, lay.cols, lay.cols)),
+            "evec": (torch.float64, (b, lay.cols, lay.rank[plane])),
+            "sigma": (torch.float64, (b, lay.rank[plane])),
+        }
+        dt, shape = shapes[name]
+        off = getattr(self.map, name)[plane]
+        n = int(np.prod(shape)) * torch.empty((), dtype=dt).element_size()
+        return self.workspace[off : off + n].view(dt).view(shape)
+
+
+def _check_encode_args(rank, quality, color_space, patch, dtype, kwargs):
+    assert (rank, quality) != (None, None), "Either 'rank' or 'quality' must be specified."
+    assert color_space in ("RGB", "YCbCr"), "`color_space` must be one of 'RGB' or 'YCbCr'."
+    if not patch:
+        raise NotImplementedError("lrf_b200: patch=False is not on the accelerated path (SURVEY §8f.3)")
+    if dtype != torch.int8:
+        raise NotImplementedError("lrf_b200: only dtype=torch.int8 factors are implemented")
+    extra = {k: v for k, v in kwargs.items() if k not in ("num_iters", "verbose")}
+    for k, v in extra.items():
+        if (k in ("l2", "l1_ratio") and v == 0) or (k == "num_levels" and v is None) or (k == "eps" and v == 1e-16):
+            continue
+        raise NotImplementedError(f"lrf_b200: QMF option {k}={v!r} is not implemented on the CUDA path")
+
+
+def _to_device_images(images: torch.Tensor, device) -> tuple[torch.Tensor, int]:
+    if images.dtype == torch.uint8:
+        return images.to(device, non_blocking=True).contiguous(), _cabi.LRFB_U8
+    return images.to(device).float().contiguous(), _cabi.LRFB_F32
+
+
+def qmf_encode_batch(images: torch.Tensor, rank=None, quality=None, color_space: str = "YCbCr",
+                     scale_factor=(0.5, 0.5), patch: bool = True, patch_size=(8, 8), bounds=(-16, 15),
+                     dtype: torch.dtype = torch.int8, return_records: bool = False, **kwargs):
+    """Batched ``qmf_encode``: images (B,3,H,W) → list of B encoded ``bytes`` (or, with
+    ``return_records``, the raw int8 factor records on the device plus the layout / metadata)."""
+    _check_encode_args(rank, quality, color_space, patch, dtype, kwargs)
+    _require_cuda()
+    assert images.ndim == 4 and images.shape[1] == 3, "images must be (B, 3, H, W)"
+    device = images.device if images.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    dev_images, in_dtype = _to_device_images(images, device)
+    B, _, H, W = images.shape
+    cfg, lay = resolve_plan(H, W, rank, quality, color_space, scale_factor, patch_size, bounds,
+                            kwargs.get("num_iters", 10), in_dtype)
+    with torch.cuda.device(device):
+        plan = EncodePlan(cfg, lay, B, device)
+        records = plan.run(dev_images)
+        meta = _metadata(images.dtype, color_space, patch, bounds, patch_size, lay)
+        if return_records:
+            return records, lay, meta
+        host = records.cpu().numpy()
+    return list(_pool().map(lambda i: packing.pack_qmf_record(host[i], lay, meta), range(B)))
+
+
+def qmf_encode(image: torch.Tensor, rank=None, quality=None, color_space: str = "YCbCr",
+               scale_factor=(0.5, 0.5), patch: bool = True, patch_size=(8, 8), bounds=(-16, 15),
+               dtype: torch.dtype = torch.int8, **kwargs) -> bytes:
+    """Drop-in for ``lrf.qmf_encode`` (lrf/compression/qmf.py:116-292)."""
+    _check_encode_args(rank, quality, color_space, patch, dtype, kwargs)
+    return qmf_encode_batch(image.unsqueeze(0), rank, quality, color_space, scale_factor, patch, patch_size,
+                            bounds, dtype, **kwargs)[0]
+
+
+def _parse_encoded(encoded: bytes):
+    """bytes → (metadata, list of fiber-major int8 arrays [U0, V0, ...])."""
+    meta_b, body = packing.separate_bytes(encoded, 2)
+    meta = packing.bytes_to_dict(meta_b)
+    n = 2 if meta["color space"] == "RGB" else 6
+    return meta, [packing.decode_fibers(b) for b in packing.separate_bytes(body, n)]
+
+
+def _decode_config(meta):
+    if not meta["patch"]:
+        raise NotImplementedError("lrf_b200: patch=False streams are not on the accelerated path")
+    if meta["dtype"] != "uint8":
+        raise NotImplementedError("lrf_b200: only uint8 images are decoded on the CUDA path")
+    ycbcr = meta["color space"] == "YCbCr"
+    (H, W) = meta["original size"][0] if ycbcr else meta["original size"]
+    ranks = meta["rank"] if ycbcr else [meta["rank"]]
+    if ycbcr:
+        ch, cw = meta["original size"][1]
+        # any scale with floor(H*s) == ch reproduces the geometry; the decoder only needs sizes
+        scale = ((ch + 0.5) / H, (cw + 0.5) / W)
+    else:
+        scale = (0.5, 0.5)
+    cfg = _cabi.make_config(H, W, meta["patch size"], meta["color space"], _cabi.LRFB_U8, scale, ranks,
+                            meta["bounds"], 1)
+    lay = _cabi.QmfLayout()
+    _cabi.check(_cabi.lib().lrfb_qmf_layout_query(C.byref(cfg), C.byref(lay)), "lrfb_qmf_layout_query")
+    if ycbcr:
+        got = [[lay.orig_h[i], lay.orig_w[i]] for i in range(3)]
+        assert got == [list(s) for s in meta["original size"]], "inconsistent plane sizes in metadata"
+        assert [[lay.pad_h[i], lay.pad_w[i]] for i in range(3)] == [list(s) for s in meta["padded size"]]
+    return cfg, lay
+
+
+def decode_records(records: torch.Tensor, cfg) -> torch.Tensor:
+    """int8 records (B, record_bytes) on the device → uint8 images (B,3,H,W) on the device."""
+    B = records.shape[0]
+    out = torch.empty((B, 3, cfg.height, cfg.width), dtype=torch.uint8, device=records.device)
+    rc = _cabi.lib().lrfb_qmf_decode(C.byref(cfg), B, C.c_void_p(records.data_ptr()),
+                                     C.c_void_p(out.data_ptr()), _stream_ptr())
+    _cabi.check(rc, "lrfb_qmf_decode")
+    return out
+
+
+def qmf_decode_batch(encoded: list[bytes], device=None) -> torch.Tensor:
+    """Batched ``qmf_decode`` of equally shaped streams → uint8 (B,3,H,W) on the device."""
+    _require_cuda()
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    parsed = list(_pool().map(_parse_encoded, encoded))
+    cfg, lay = _decode_config(parsed[0][0])
+    host = np.empty((len(encoded), lay.record_bytes), np.int8)
+    for i, (_, fibers) in enumerate(parsed):
+        for pl in range(lay.n_planes):
+            u, v = fibers[2 * pl], fibers[2 * pl + 1]
+            host[i, lay.u_offset[pl] : lay.u_offset[pl] + u.size] = u.reshape(-1)
+            host[i, lay.v_offset[pl] : lay.v_offset[pl] + v.size] = v.reshape(-1)
+    with torch.cuda.device(device):
+        return decode_records(torch.from_numpy(host).to(device), cfg)
+
+
+def qmf_decode(encoded_image: bytes) -> torch.Tensor:
+    """Drop-in for ``lrf.qmf_decode`` (lrf/compression/qmf.py:295-353): returns a CPU uint8 (3,H,W)."""
+    return qmf_decode_batch([encoded_image])[0].cpu()
+
+
+def sse_u8(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """Exact per-image sum of squared differences of two uint8 batches on the device."""
+    assert a.shape == b.shape and a.dtype == torch.uint8 and b.dtype == torch.uint8 and a.is_cuda
+    a, b = a.contiguous(), b.contiguous()
+    B = a.shape[0]
+    out = torch.zeros(B, dtype=torch.int64, device=a.device)
+    rc = _cabi.lib().lrfb_sse_u8(C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), a[0].numel(), B,
+                                 C.c_void_p(out.data_ptr()), _stream_ptr())
+    _cabi.check(rc, "lrfb_sse_u8")
+    return out
+
+
+def psnr_batch(a: torch.Tensor, b: torch.Tensor, max_value: float = 255.0) -> torch.Tensor:
+    """lrf/utils/metrics.py:57-71 per image, from the exact integer SSE."""
+    mse = sse_u8(a, b).double() / a[0].numel()
+    return 20 * torch.log10(max_value / torch.sqrt(mse))

@@ -1,0 +1,57 @@
+"""CPU-only: the host byte packing reproduces the reference's encoded-object layout byte for byte."""
+import ctypes as C
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_bytes, golden_kwargs
+from lrf_b200 import _cabi, compression, packing
+from lrf_b200.build import build
+from oracle import qmf_port as port
+
+CASES = ["kodim01_q7", "snat1000_512x768_q7", "snat7_45x70_q7", "snat8_101x131_q7", "snat1000_256x384_p4",
+         "snat1000_256x384_p16", "snat1000_256x384_rank", "snat1000_128x192_rgb", "snat1000_256x384_b128"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_repack_golden_factors_is_byte_identical(manifest, name):
+    build()
+    e = manifest["cases"][name]
+    kw = golden_kwargs(e)
+    blob = golden_bytes(name)
+    meta, fibers = compression._parse_encoded(blob)
+    ycbcr = meta["color space"] == "YCbCr"
+    H, W = meta["original size"][0] if ycbcr else meta["original size"]
+    cfg, lay = compression.resolve_plan(H, W, kw.get("rank"), kw.get("quality"), kw["color_space"],
+                                        kw["scale_factor"], kw["patch_size"], kw["bounds"], kw["num_iters"])
+    assert [lay.rank[i] for i in range(lay.n_planes)] == (meta["rank"] if ycbcr else [meta["rank"]])
+    rec = np.zeros(lay.record_bytes, np.int8)
+    for pl in range(lay.n_planes):
+        u, v = fibers[2 * pl], fibers[2 * pl + 1]
+        rec[lay.u_offset[pl] : lay.u_offset[pl] + u.size] = u.reshape(-1)
+        rec[lay.v_offset[pl] : lay.v_offset[pl] + v.size] = v.reshape(-1)
+    new_meta = compression._metadata(torch.uint8, kw["color_space"], True, kw["bounds"], kw["patch_size"], lay)
+    assert json.dumps(new_meta) == json.dumps(meta)
+    assert packing.pack_qmf_record(rec, lay, new_meta) == blob
+
+
+def test_framing_errors_match_reference_behaviour():
+    with pytest.raises(TypeError):
+        packing.combine_bytes([b"a", "b"])
+    with pytest.raises(ValueError):
+        packing.separate_bytes(b"\x00\x01", 2)
+    parts = [b"x" * 5, b"", b"yz"]
+    assert list(packing.separate_bytes(packing.combine_bytes(parts), 3)) == parts
+    assert packing.combine_bytes(parts) == port.combine_bytes(parts)
+
+
+def test_argument_errors_match_reference():
+    img = torch.zeros(3, 16, 16, dtype=torch.uint8)
+    with pytest.raises(AssertionError):
+        compression.qmf_encode(img)
+    with pytest.raises(AssertionError):
+        compression.qmf_encode(img, quality=7, color_space="HSV")
+    with pytest.raises(NotImplementedError):
+        compression.qmf_encode(img, quality=7, patch=False)
