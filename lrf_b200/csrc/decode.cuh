@@ -77,6 +77,91 @@ qmf_decode_kernel(const int8_t* __restrict__ factors, unsigned char* __restrict_
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Fast path: YCbCr, 8x8 patches, W % 16 == 0, chroma width == W/2.  One thread reconstructs 8
+// consecutive pixels of one image row: they lie in one luma patch row and 4 consecutive elements of one
+// chroma patch row, so the factors are read as 8-byte / 4-byte vectors and each colour plane gets one
+// 8-byte store.  Same arithmetic as qmf_decode_kernel.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sbyte_of(unsigned w, int k) { return (float)(signed char)((w >> (8 * k)) & 0xffu); }
+
+__global__ void __launch_bounds__(256)
+qmf_decode8_kernel(const int8_t* __restrict__ factors, unsigned char* __restrict__ out, DecodeParams P) {
+  const float t[3][3] = {{1.0f, 0.0f, 1.40200f}, {1.0f, -0.344136f, -0.714136f}, {1.0f, 1.77200f, 0.0f}};
+  const size_t hw = (size_t)P.H * P.W;
+  const int segs = P.W / 8;
+  const long long items = (long long)P.H * segs;
+  const PlaneGeom gy = P.g[0], gc = P.g[1];
+  const int shy = (gy.hp - gy.h) / 2, shc = (gc.hp - gc.h) / 2;
+  for (int im = blockIdx.y; im < P.n_img; im += gridDim.y) {
+    const int8_t* rec = factors + (size_t)im * P.record_bytes;
+    unsigned char* o = out + (size_t)im * 3 * hw;
+    for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items;
+         it += (long long)gridDim.x * blockDim.x) {
+      const int y = (int)(it / segs), sg = (int)(it - (long long)y * segs);
+      float py[8], pcb[4], pcr[4];
+      {  // luma
+        const int yy = y + shy, m = (yy >> 3) * gy.nbw + sg, col = (yy & 7) * 8;
+        const int8_t* u = rec + P.u_off[0];
+        const int8_t* v = rec + P.v_off[0];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) py[j] = 0.0f;
+        for (int r = 0; r < P.rank[0]; ++r) {
+          const float ur = (float)u[(size_t)r * gy.rows + m];
+          const uint2 vv = *reinterpret_cast<const uint2*>(v + (size_t)r * 64 + col);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            py[j] = __fadd_rn(py[j], __fmul_rn(ur, sbyte_of(vv.x, j)));
+            py[4 + j] = __fadd_rn(py[4 + j], __fmul_rn(ur, sbyte_of(vv.y, j)));
+          }
+        }
+      }
+      {  // chroma: pixels 8*sg .. 8*sg+7 use chroma columns 4*sg .. 4*sg+3
+        const int sy = nearest_src(y, gc.h, P.H);
+        const int yy = sy + shc, cx0 = 4 * sg;
+        const int m = (yy >> 3) * gc.nbw + (cx0 >> 3), col = (yy & 7) * 8 + (cx0 & 7);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pcb[j] = 0.0f, pcr[j] = 0.0f;
+        for (int r = 0; r < P.rank[1]; ++r) {
+          const float ur = (float)rec[P.u_off[1] + (size_t)r * gc.rows + m];
+          const unsigned vv = *reinterpret_cast<const unsigned*>(rec + P.v_off[1] + (size_t)r * 64 + col);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) pcb[j] = __fadd_rn(pcb[j], __fmul_rn(ur, sbyte_of(vv, j)));
+        }
+        for (int r = 0; r < P.rank[2]; ++r) {
+          const float ur = (float)rec[P.u_off[2] + (size_t)r * gc.rows + m];
+          const unsigned vv = *reinterpret_cast<const unsigned*>(rec + P.v_off[2] + (size_t)r * 64 + col);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) pcr[j] = __fadd_rn(pcr[j], __fmul_rn(ur, sbyte_of(vv, j)));
+        }
+      }
+      unsigned lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float y0 = __fadd_rn(py[j], 0.0f);
+        const float cb = __fadd_rn(pcb[j >> 1], -128.0f), cr = __fadd_rn(pcr[j >> 1], -128.0f);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float acc = __fmul_rn(t[c][0], y0);
+          acc = __fmaf_rn(t[c][1], cb, acc);
+          acc = __fmaf_rn(t[c][2], cr, acc);
+          const unsigned b = to_u8_trunc(acc);
+          if (j < 4) lo[c] |= b << (8 * j);
+          else hi[c] |= b << (8 * (j - 4));
+        }
+      }
+      const size_t off = (size_t)y * P.W + (size_t)sg * 8;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        uint2 w;
+        w.x = lo[c], w.y = hi[c];
+        *reinterpret_cast<uint2*>(o + c * hw + off) = w;
+      }
+    }
+  }
+}
+
 // exact sum of squared differences per image: integer arithmetic, order-independent
 __global__ void __launch_bounds__(256)
 sse_u8_kernel(const unsigned char* __restrict__ a, const unsigned char* __restrict__ b, long long per_img,

@@ -86,4 +86,108 @@ frontend_kernel(const in_t* __restrict__ images, float* __restrict__ xout, Front
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Fast path: uint8 input, YCbCr, 8x8 patches, W % 16 == 0 and chroma width == W/2 (no horizontal
+// padding on any plane, 2-wide pooling windows).  One thread produces 8 consecutive elements of one
+// patch row: 8-byte (Y) / 16-byte (chroma) vector loads per channel, 2 x 16-byte stores.  Same
+// arithmetic, operation for operation, as frontend_kernel.
+// ---------------------------------------------------------------------------------------------------
+namespace {
+__device__ __forceinline__ float ycc_from(float r, float g, float b, int c) {
+  // c is a compile-time constant at every call site
+  const float t0 = c == 0 ? 0.299f : c == 1 ? -0.168736f : 0.5f;
+  const float t1 = c == 0 ? 0.587f : c == 1 ? -0.331264f : -0.418688f;
+  const float t2 = c == 0 ? 0.114f : c == 1 ? 0.5f : -0.081312f;
+  const float off = c == 0 ? 0.0f : 128.0f;
+  float acc = __fmul_rn(t0, r);
+  acc = __fmaf_rn(t1, g, acc);
+  acc = __fmaf_rn(t2, b, acc);
+  return __fadd_rn(off, acc);
+}
+__device__ __forceinline__ float byte_of(unsigned w, int k) { return (float)((w >> (8 * k)) & 0xffu); }
+}  // namespace
+
+__global__ void __launch_bounds__(256)
+frontend8_luma_kernel(const unsigned char* __restrict__ images, float* __restrict__ xout, FrontParams P) {
+  const PlaneGeom g = P.g[0];
+  const size_t hw = (size_t)P.H * P.W;
+  const int nbw = g.nbw;  // == W/8
+  const long long items = (long long)g.hp * nbw;
+  for (int im = blockIdx.y; im < P.n_img; im += gridDim.y) {
+    const unsigned char* img = images + (size_t)im * 3 * hw;
+    float* x = xout + (size_t)im * g.rows * 64;
+    for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items;
+         it += (long long)gridDim.x * blockDim.x) {
+      const int yy = (int)(it / nbw), wb = (int)(it - (long long)yy * nbw);
+      const int y = reflect_idx(yy - g.top, g.h);
+      const size_t off = (size_t)y * P.W + (size_t)wb * 8;
+      const uint2 r = *reinterpret_cast<const uint2*>(img + off);
+      const uint2 gg = *reinterpret_cast<const uint2*>(img + hw + off);
+      const uint2 b = *reinterpret_cast<const uint2*>(img + 2 * hw + off);
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        o[k] = ycc_from(byte_of(r.x, k), byte_of(gg.x, k), byte_of(b.x, k), 0);
+        o[4 + k] = ycc_from(byte_of(r.y, k), byte_of(gg.y, k), byte_of(b.y, k), 0);
+      }
+      float* dst = x + ((size_t)(yy >> 3) * nbw + wb) * 64 + (yy & 7) * 8;
+      *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+frontend8_chroma_kernel(const unsigned char* __restrict__ images, float* __restrict__ xcb,
+                        float* __restrict__ xcr, FrontParams P) {
+  const PlaneGeom g = P.g[1];
+  const size_t hw = (size_t)P.H * P.W;
+  const int nbw = g.nbw;  // == W/16
+  const long long items = (long long)g.hp * nbw;
+  for (int im = blockIdx.y; im < P.n_img; im += gridDim.y) {
+    const unsigned char* img = images + (size_t)im * 3 * hw;
+    float* ocb = xcb + (size_t)im * g.rows * 64;
+    float* ocr = xcr + (size_t)im * g.rows * 64;
+    for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items;
+         it += (long long)gridDim.x * blockDim.x) {
+      const int yy = (int)(it / nbw), wb = (int)(it - (long long)yy * nbw);
+      const int cy = reflect_idx(yy - g.top, g.h);
+      const int h0 = (int)(((long long)cy * P.H) / g.h);
+      const int h1 = (int)(((long long)(cy + 1) * P.H + g.h - 1) / g.h);
+      float sb[8], sr[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sb[j] = 0.0f, sr[j] = 0.0f;
+      for (int row = h0; row < h1; ++row) {
+        const size_t off = (size_t)row * P.W + (size_t)wb * 16;
+        const uint4 r = *reinterpret_cast<const uint4*>(img + off);
+        const uint4 gg = *reinterpret_cast<const uint4*>(img + hw + off);
+        const uint4 b = *reinterpret_cast<const uint4*>(img + 2 * hw + off);
+        const unsigned rw[4] = {r.x, r.y, r.z, r.w}, gw[4] = {gg.x, gg.y, gg.z, gg.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            const int px = 2 * j + s;
+            const float fr = byte_of(rw[px >> 2], px & 3), fg = byte_of(gw[px >> 2], px & 3),
+                        fb = byte_of(bw[px >> 2], px & 3);
+            sb[j] = __fadd_rn(sb[j], ycc_from(fr, fg, fb, 1));
+            sr[j] = __fadd_rn(sr[j], ycc_from(fr, fg, fb, 2));
+          }
+        }
+      }
+      const float kh = (float)(h1 - h0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        sb[j] = __fdiv_rn(__fdiv_rn(sb[j], kh), 2.0f);
+        sr[j] = __fdiv_rn(__fdiv_rn(sr[j], kh), 2.0f);
+      }
+      const size_t o = ((size_t)(yy >> 3) * nbw + wb) * 64 + (yy & 7) * 8;
+      *reinterpret_cast<float4*>(ocb + o) = make_float4(sb[0], sb[1], sb[2], sb[3]);
+      *reinterpret_cast<float4*>(ocb + o + 4) = make_float4(sb[4], sb[5], sb[6], sb[7]);
+      *reinterpret_cast<float4*>(ocr + o) = make_float4(sr[0], sr[1], sr[2], sr[3]);
+      *reinterpret_cast<float4*>(ocr + o + 4) = make_float4(sr[4], sr[5], sr[6], sr[7]);
+    }
+  }
+}
+
 }  // namespace lrfb

@@ -6,7 +6,8 @@
 // Mapping: the upper triangle of G is cut into 4x4 blocks; each thread owns up to BPT blocks
 // (16 DFMA per block per row), rows are staged through shared memory already converted to f64
 // (one F2F per element instead of one per use).  grid = (row splits, matrices); a split writes a
-// partial Gram which gram_reduce_kernel sums in fixed order.
+// partial Gram which gram_reduce_kernel sums in fixed order; grid.z cuts the block list when one CTA's
+// registers cannot hold all of it (N = 256).
 #pragma once
 #include "lrfb_common.cuh"
 
@@ -15,7 +16,8 @@ namespace lrfb {
 constexpr int kGramTileRows = 16;
 
 template <int BPT>
-__global__ void gram_kernel(const float* __restrict__ X, long long x_stride, int M, int N,
+__global__ void __launch_bounds__(256)
+gram_kernel(const float* __restrict__ X, long long x_stride, int M, int N,
                             double* __restrict__ Gout, int n_split) {
   LRFB_DYN_SMEM(smem_raw);
   double* tile = reinterpret_cast<double*>(smem_raw);  // [kGramTileRows][Npad]
@@ -29,7 +31,7 @@ __global__ void gram_kernel(const float* __restrict__ X, long long x_stride, int
   double acc[BPT][16];
 #pragma unroll
   for (int b = 0; b < BPT; ++b) {
-    int idx = threadIdx.x + b * blockDim.x;
+    int idx = blockIdx.z * (blockDim.x * BPT) + threadIdx.x + b * blockDim.x;
     bi[b] = -1, bj[b] = 0;
     if (idx < nblocks) {  // idx -> (i, j), i <= j, row-major over the upper triangle
       int i = 0, rem = idx;

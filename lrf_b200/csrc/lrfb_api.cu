@@ -164,9 +164,10 @@ struct FactorWs {  // scratch beyond x/u/v/gram/evec/sigma
 
 template <int BPT>
 void launch_gram(const float* x, long long xs, int M, int N, double* out, int split, int n_mat, int threads,
-                 cudaStream_t st) {
+                 int nblocks, cudaStream_t st) {
   size_t smem = (size_t)kGramTileRows * ((N + 3) & ~3) * 8;
-  LRFB_LAUNCH(gram_kernel<BPT>, dim3(split, n_mat), dim3(threads), smem, st, x, xs, M, N, out, split);
+  int gz = (nblocks + threads * BPT - 1) / (threads * BPT);
+  LRFB_LAUNCH(gram_kernel<BPT>, dim3(split, n_mat, gz), dim3(threads), smem, st, x, xs, M, N, out, split);
 }
 
 template <int R>
@@ -230,11 +231,10 @@ int factorize_batch(const float* x, int n_mat, int M, int N, int R, float lo, fl
       const float* xx = x + (size_t)m0 * M * N;
       double* go = gout + (size_t)m0 * split * N * N;
       if (nblocks <= 160) {
-        launch_gram<1>(xx, (long long)M * N, M, N, go, split, cnt, ((nblocks + 31) / 32) * 32, st);
+        launch_gram<1>(xx, (long long)M * N, M, N, go, split, cnt, ((nblocks + 31) / 32) * 32, nblocks, st);
       } else {
-        int threads = std::min(512, (((nblocks + 4) / 5 + 31) / 32) * 32);
-        if ((long long)threads * 5 < nblocks) return fail(LRFB_E_UNSUPPORTED, "N=%d too large for gram", N);
-        launch_gram<5>(xx, (long long)M * N, M, N, go, split, cnt, threads, st);
+        int threads = std::min(256, (((nblocks + 4) / 5 + 31) / 32) * 32);
+        launch_gram<5>(xx, (long long)M * N, M, N, go, split, cnt, threads, nblocks, st);
       }
       if ((rc = check_launch("gram_kernel"))) return rc;
       if (split > 1) {
@@ -275,8 +275,27 @@ int64_t encode_scratch_bytes(const Geometry& g, int batch) {
   return mx;
 }
 
+// vectorised kernels apply: 8x8 patches, YCbCr, W % 16 == 0, chroma exactly half width, aligned base
+bool fast8_geometry(const Geometry& g, const void* base) {
+  const FrontParams& f = g.fp;
+  return f.ycbcr && f.p == 8 && f.q == 8 && f.W % 16 == 0 && f.g[1].w * 2 == f.W &&
+         ((uintptr_t)base % 16) == 0;
+}
+
 int run_frontend(const lrfb_qmf_config* cfg, const Geometry& g, int batch, const void* d_images,
                  float* const* xs, cudaStream_t st) {
+  if (cfg->input_dtype == LRFB_U8 && fast8_geometry(g, d_images)) {
+    const unsigned char* img = (const unsigned char*)d_images;
+    long long items = (long long)g.fp.g[0].hp * g.fp.g[0].nbw;
+    dim3 grid((unsigned)std::min<long long>((items + 255) / 256, 4096), std::min(batch, 65535));
+    LRFB_LAUNCH(frontend8_luma_kernel, grid, dim3(256), 0, st, img, xs[0], g.fp);
+    int rc = check_launch("frontend8_luma_kernel");
+    if (rc) return rc;
+    items = (long long)g.fp.g[1].hp * g.fp.g[1].nbw;
+    dim3 grid2((unsigned)std::min<long long>((items + 255) / 256, 4096), std::min(batch, 65535));
+    LRFB_LAUNCH(frontend8_chroma_kernel, grid2, dim3(256), 0, st, img, xs[1], xs[2], g.fp);
+    return check_launch("frontend8_chroma_kernel");
+  }
   for (int pl = 0; pl < g.lay.n_planes; ++pl) {
     long long per_img = (long long)g.lay.rows[pl] * g.lay.cols;
     int gx = (int)std::min<long long>((per_img + 255) / 256, 8192);
@@ -423,6 +442,13 @@ LRFB_EXPORT int32_t lrfb_qmf_decode(const lrfb_qmf_config* cfg, int32_t batch, c
   }
   long long hw = (long long)cfg->height * cfg->width;
   dim3 grid((unsigned)std::min<long long>((hw + 255) / 256, 8192), std::min(batch, 65535));
+  if (fast8_geometry(g, d_images) && g.lay.record_bytes % 8 == 0 && ((uintptr_t)d_factors % 8) == 0 &&
+      g.lay.v_offset[0] % 8 == 0 && g.lay.v_offset[1] % 4 == 0 && g.lay.v_offset[2] % 4 == 0) {
+    long long items = hw / 8;
+    dim3 grid8((unsigned)std::min<long long>((items + 255) / 256, 4096), std::min(batch, 65535));
+    LRFB_LAUNCH(qmf_decode8_kernel, grid8, dim3(256), 0, (cudaStream_t)(uintptr_t)stream, d_factors, d_images, P);
+    return check_launch("qmf_decode8_kernel");
+  }
   LRFB_LAUNCH(qmf_decode_kernel, grid, dim3(256), 0, (cudaStream_t)(uintptr_t)stream, d_factors, d_images, P);
   return check_launch("qmf_decode_kernel");
 }
