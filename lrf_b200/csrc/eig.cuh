@@ -2,48 +2,57 @@
 // stage two of the SVD initialisation (replaces LAPACK gesdd behind torch.linalg.svd,
 // lrf/factorization/qmf.py:44-45; only the top R of the N triplets are ever used).
 //
-// One CTA per matrix, all FP64:
-//   1. Householder tridiagonalisation (reflectors kept in place, LAPACK dsytrd/dlarfg conventions)
-//   2. the R largest eigenvalues by multisection on Sturm counts (16 probes per eigenvalue per round)
-//   3. eigenvectors of the tridiagonal by inverse iteration (pivoted tridiagonal LU), MGS clean-up
+// One WARP per matrix (one-warp CTAs; the batch supplies the parallelism), all FP64:
+//   1. Householder tridiagonalisation (LAPACK dsytrd/dlarfg conventions); lane l owns columns
+//      l, l+32, ...; the matrix is symmetric, so every access is row-contiguous (bank-conflict free in
+//      shared memory, coalesced in global memory); reflector k is kept in the dead row k
+//   2. the R largest eigenvalues by warp-wide multisection on division-free Sturm sequences
+//   3. eigenvectors of the tridiagonal by inverse iteration (pivoted LU as in dgttrf), MGS clean-up
 //   4. back-transformation through the reflectors, sign convention, sigma = sqrt(lambda)
-// The matrix is accessed column-per-thread (it is symmetric), so the same code runs with the matrix in
-// shared memory (N <= 80) or in global memory (larger N) without bank conflicts / uncoalesced access.
-// Every phase is "each thread owns index t, barrier, next phase" with dot products recomputed
-// redundantly per thread in a fixed order: deterministic and independent of the thread count.
+// Reductions are xor-butterflies (every lane ends with the same bits); nothing depends on timing.
+// For N <= 64 and R <= 4 the matrix and all scratch live in shared memory, otherwise in global memory.
 #pragma once
 #include "lrfb_common.cuh"
 
 namespace lrfb {
 
-constexpr int kEigProbes = 16;   // probes per eigenvalue per multisection round
-constexpr int kEigRounds = 16;   // 17^16 > 2^64: interval shrinks below one ulp of ||T||
 constexpr int kEigMaxR = 32;
 
-struct EigScratch {  // per matrix, in global memory (doubles)
-  // layout: d[N], e[N], tau[N], vv[N], p[N], w[N], lam[kEigMaxR], part[kEigMaxR*16],
-  //         z[R][N], lu[R][5N]
+struct EigScratch {  // per matrix (doubles): d, e, tau, vv, w [5N] | lam [32] | z [R][N] | lu [R][5N]
   static __host__ __device__ size_t doubles(int N, int R) {
-    return (size_t)6 * N + kEigMaxR + kEigMaxR * 16 + (size_t)R * N + (size_t)R * 5 * N + 64;
+    return (size_t)5 * N + kEigMaxR + (size_t)R * N + (size_t)R * 5 * N + 8;
   }
+  static __host__ __device__ bool fits_shared(int N, int R) { return N <= 64 && R <= 4; }
 };
 
-// Sturm count: number of eigenvalues of tridiag(d, e) strictly below x
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Number of eigenvalues of tridiag(d, e) strictly below x: sign changes of the leading principal
+// minors p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2}, rescaled by powers of two.  Equivalent to the
+// pivot recurrence of LAPACK dlaebz (q_i = p_i / p_{i-1}, |q| < pivmin -> -pivmin) without divisions.
 __device__ inline int sturm_count(const double* d, const double* e, int N, double x, double pivmin) {
-  int cnt = 0;
-  double q = d[0] - x;
-  if (fabs(q) < pivmin) q = -pivmin;
-  cnt += q < 0.0;
+  double pm = 1.0;  // p_{i-1}
+  double p = d[0] - x;
+  if (fabs(p) < pivmin) p = -pivmin;
+  int cnt = p < 0.0;
   for (int i = 1; i < N; ++i) {
-    q = d[i] - x - e[i - 1] * e[i - 1] / q;
-    if (fabs(q) < pivmin) q = -pivmin;
-    cnt += q < 0.0;
+    double pn = fma(d[i] - x, p, -(e[i - 1] * e[i - 1]) * pm);
+    if (fabs(pn) < pivmin * fabs(p)) pn = -pivmin * p;
+    cnt += (pn < 0.0) != (p < 0.0);
+    pm = p, p = pn;
+    double a = fabs(p);
+    if (a > 1e100) pm *= 1e-100, p *= 1e-100;
+    else if (a < 1e-100) pm *= 1e100, p *= 1e100;
   }
   return cnt;
 }
 
 // Inverse iteration for one eigenvector of tridiag(d, e) at shift lam; z (N) receives a unit vector.
-// lu: 5N doubles of scratch.  Pivoted LU as in LAPACK dgttrf / dgtts2.
+// lu: 5N doubles of scratch.  Pivoted LU as in LAPACK dgttrf / dgtts2, pivots stored as reciprocals.
 __device__ inline void tridiag_inverse_iteration(const double* d, const double* e, int N, double lam,
                                                  double tnorm, double* z, double* lu, int seed) {
   double* dl = lu;
@@ -61,12 +70,15 @@ __device__ inline void tridiag_inverse_iteration(const double* d, const double* 
   for (int i = 0; i < N - 1; ++i) {
     if (fabs(dd[i]) >= fabs(dl[i])) {
       if (fabs(dd[i]) < tol) dd[i] = (dd[i] < 0.0) ? -tol : tol;
-      double f = dl[i] / dd[i];
+      double rc = 1.0 / dd[i];
+      double f = dl[i] * rc;
       dl[i] = f;
       dd[i + 1] -= f * du[i];
+      dd[i] = rc;
     } else {
-      double f = dd[i] / dl[i];
-      dd[i] = dl[i];
+      double rc = 1.0 / dl[i];
+      double f = dd[i] * rc;
+      dd[i] = rc;
       dl[i] = f;
       double t = du[i];
       du[i] = dd[i + 1];
@@ -79,6 +91,7 @@ __device__ inline void tridiag_inverse_iteration(const double* d, const double* 
     }
   }
   if (fabs(dd[N - 1]) < tol) dd[N - 1] = (dd[N - 1] < 0.0) ? -tol : tol;
+  dd[N - 1] = 1.0 / dd[N - 1];
 
   unsigned s = 12345u + 7919u * (unsigned)seed;
   for (int i = 0; i < N; ++i) {  // deterministic start vector with no special structure
@@ -95,90 +108,96 @@ __device__ inline void tridiag_inverse_iteration(const double* d, const double* 
         z[i + 1] = t - dl[i] * z[i];
       }
     }
-    z[N - 1] /= dd[N - 1];
-    if (N > 1) z[N - 2] = (z[N - 2] - du[N - 2] * z[N - 1]) / dd[N - 2];
-    for (int i = N - 3; i >= 0; --i) z[i] = (z[i] - du[i] * z[i + 1] - du2[i] * z[i + 2]) / dd[i];
+    z[N - 1] *= dd[N - 1];
+    if (N > 1) z[N - 2] = (z[N - 2] - du[N - 2] * z[N - 1]) * dd[N - 2];
+    for (int i = N - 3; i >= 0; --i) z[i] = (z[i] - du[i] * z[i + 1] - du2[i] * z[i + 2]) * dd[i];
     double mx = 0.0;
     for (int i = 0; i < N; ++i) mx = fmax(mx, fabs(z[i]));
     if (!(mx > 0.0) || !(mx < 1e300)) {  // breakdown guard: restart from a basis vector
       for (int i = 0; i < N; ++i) z[i] = (i == seed % N) ? 1.0 : 0.0;
       mx = 1.0;
     }
-    double nrm = 0.0;
+    double inv = 1.0 / mx, nrm = 0.0;
     for (int i = 0; i < N; ++i) {
-      z[i] /= mx;
-      nrm += z[i] * z[i];
+      z[i] *= inv;
+      nrm = fma(z[i], z[i], nrm);
     }
     nrm = 1.0 / sqrt(nrm);
     for (int i = 0; i < N; ++i) z[i] *= nrm;
   }
 }
 
-// One CTA per matrix.  A: N x N symmetric (overwritten), either shared (a_shared) or global.
-// Outputs per matrix: evec[N][R] (unit, sign-fixed, row-major) and sigma[R] = sqrt(max(lambda,0)).
-// sign_flip: optional per-matrix R ints (+1/-1) multiplied onto the convention (test hook, may be null).
-__global__ void eig_topr_kernel(const double* __restrict__ Gin, int N, int R, double* __restrict__ scratch_all,
-                                double* __restrict__ evec_out, double* __restrict__ sigma_out,
-                                const int* __restrict__ sign_flip, int use_shared) {
+// One warp (= one CTA of 32 threads) per matrix.  Gin: [n][N][N] symmetric (overwritten when the
+// working copy stays in global memory).  Outputs per matrix: evec[N][R] (unit, sign-fixed, row-major)
+// and sigma[R] = sqrt(max(lambda, 0)).  sign_flip: optional [n][R] of +1/-1 multiplied onto the
+// convention (test hook, may be null).
+__global__ void __launch_bounds__(32)
+eig_topr_kernel(const double* __restrict__ Gin, int N, int R, double* __restrict__ scratch_all,
+                double* __restrict__ evec_out, double* __restrict__ sigma_out,
+                const int* __restrict__ sign_flip, int use_shared) {
   LRFB_DYN_SMEM(smem_raw);
   const int mat = blockIdx.x;
-  const int T = blockDim.x;
-  const int t = threadIdx.x;
-  double* scratch = scratch_all + (size_t)mat * EigScratch::doubles(N, R);
+  const int lane = threadIdx.x;
+  double* A;
+  double* scratch;
+  if (use_shared) {
+    A = reinterpret_cast<double*>(smem_raw);
+    scratch = A + (size_t)N * N;
+    const double* g = Gin + (size_t)mat * N * N;
+    for (int i = lane; i < N * N; i += 32) A[i] = g[i];
+  } else {
+    A = const_cast<double*>(Gin) + (size_t)mat * N * N;
+    scratch = scratch_all + (size_t)mat * EigScratch::doubles(N, R);
+  }
   double* d = scratch;
   double* e = d + N;
   double* tau = e + N;
   double* vv = tau + N;
-  double* p = vv + N;
-  double* w = p + N;
+  double* w = vv + N;
   double* lam = w + N;
-  double* part = lam + kEigMaxR;
-  double* z = part + kEigMaxR * 16;
+  double* z = lam + kEigMaxR;
   double* lu = z + (size_t)R * N;
-  // the working copy of the matrix
-  double* A = use_shared ? reinterpret_cast<double*>(smem_raw)
-                         : const_cast<double*>(Gin) + (size_t)mat * N * N;
-  if (use_shared) {
-    const double* g = Gin + (size_t)mat * N * N;
-    for (int i = t; i < N * N; i += T) A[i] = g[i];
-  }
-  __syncthreads();
+  __syncwarp();
 
   // ---- 1. tridiagonalisation -------------------------------------------------------------------
   for (int k = 0; k < N - 2; ++k) {
-    // reflector for x = A[k+1.., k]; every thread derives the same scalars (broadcast reads)
-    double alpha0 = A[(size_t)(k + 1) * N + k];
-    double xn2 = 0.0;
-    for (int i = k + 2; i < N; ++i) {
-      double a = A[(size_t)i * N + k];
-      xn2 = fma(a, a, xn2);
-    }
+    const double* rowk = A + (size_t)k * N;  // x = A[k][k+1..] (= column k by symmetry)
+    const double alpha0 = rowk[k + 1];
+    double part = 0.0;
+    for (int c = k + 2 + lane; c < N; c += 32) part = fma(rowk[c], rowk[c], part);
+    const double xn2 = warp_sum(part);
     double beta, tk, scal;
     if (xn2 == 0.0) {
       beta = alpha0, tk = 0.0, scal = 0.0;
     } else {
-      double nrm = sqrt(fma(alpha0, alpha0, xn2));
+      const double nrm = sqrt(fma(alpha0, alpha0, xn2));
       beta = alpha0 >= 0.0 ? -nrm : nrm;
       tk = (beta - alpha0) / beta;
       scal = 1.0 / (alpha0 - beta);
     }
-    for (int i = k + 1 + t; i < N; i += T) vv[i] = (i == k + 1) ? 1.0 : A[(size_t)i * N + k] * scal;
-    if (t == 0) d[k] = A[(size_t)k * N + k], e[k] = beta, tau[k] = tk;
-    __syncthreads();
+    for (int c = k + 1 + lane; c < N; c += 32) vv[c] = (c == k + 1) ? 1.0 : rowk[c] * scal;
+    if (lane == 0) d[k] = rowk[k], e[k] = beta, tau[k] = tk;
+    __syncwarp();
     if (tk != 0.0) {
-      for (int c = k + 1 + t; c < N; c += T) {  // p = tau * A22 v  (column c of the symmetric block)
-        double s = 0.0;
-        for (int j = k + 1; j < N; ++j) s = fma(A[(size_t)j * N + c], vv[j], s);
-        p[c] = tk * s;
+      // p = tau * A22 v, kept in w[] for now
+      double kpart = 0.0;
+      for (int c = k + 1 + lane; c < N; c += 32) {
+        double s0 = 0.0, s1 = 0.0;
+        int j = k + 1;
+        for (; j + 1 < N; j += 2) {
+          s0 = fma(A[(size_t)j * N + c], vv[j], s0);
+          s1 = fma(A[(size_t)(j + 1) * N + c], vv[j + 1], s1);
+        }
+        if (j < N) s0 = fma(A[(size_t)j * N + c], vv[j], s0);
+        const double pc = tk * (s0 + s1);
+        w[c] = pc;
+        kpart = fma(pc, vv[c], kpart);
       }
-      __syncthreads();
-      double kk = 0.0;
-      for (int j = k + 1; j < N; ++j) kk = fma(p[j], vv[j], kk);
-      kk *= 0.5 * tk;
-      for (int c = k + 1 + t; c < N; c += T) w[c] = p[c] - kk * vv[c];
-      __syncthreads();
-      for (int c = k + 1 + t; c < N; c += T) {  // A22 -= v w^T + w v^T
-        double vc = vv[c], wc = w[c];
+      const double kk = 0.5 * tk * warp_sum(kpart);
+      for (int c = k + 1 + lane; c < N; c += 32) w[c] = fma(-kk, vv[c], w[c]);
+      __syncwarp();
+      for (int c = k + 1 + lane; c < N; c += 32) {  // A22 -= v w^T + w v^T
+        const double vc = vv[c], wc = w[c];
         for (int j = k + 1; j < N; ++j) {
           double a = A[(size_t)j * N + c];
           a = fma(-vv[j], wc, a);
@@ -187,25 +206,25 @@ __global__ void eig_topr_kernel(const double* __restrict__ Gin, int N, int R, do
         }
       }
     }
-    __syncthreads();
-    for (int i = k + 1 + t; i < N; i += T) A[(size_t)i * N + k] = vv[i];  // keep the reflector in column k
-    __syncthreads();
+    __syncwarp();
+    for (int c = k + 1 + lane; c < N; c += 32) A[(size_t)k * N + c] = vv[c];  // keep reflector k in row k
+    __syncwarp();
   }
-  if (t == 0) {
+  if (lane == 0) {
     if (N >= 2) {
       d[N - 2] = A[(size_t)(N - 2) * N + (N - 2)];
-      e[N - 2] = A[(size_t)(N - 1) * N + (N - 2)];
+      e[N - 2] = A[(size_t)(N - 2) * N + (N - 1)];
       tau[N - 2] = 0.0;
     }
     d[N - 1] = A[(size_t)(N - 1) * N + (N - 1)];
     e[N - 1] = 0.0;
     tau[N - 1] = 0.0;
   }
-  __syncthreads();
+  __syncwarp();
 
   // ---- 2. R largest eigenvalues by multisection ------------------------------------------------
   double glo = d[0], ghi = d[0], maxe2 = 0.0;
-  for (int i = 0; i < N; ++i) {  // Gershgorin bounds, redundantly per thread
+  for (int i = 0; i < N; ++i) {  // Gershgorin bounds, redundantly per lane
     double r = (i > 0 ? fabs(e[i - 1]) : 0.0) + (i < N - 1 ? fabs(e[i]) : 0.0);
     glo = fmin(glo, d[i] - r);
     ghi = fmax(ghi, d[i] + r);
@@ -215,44 +234,40 @@ __global__ void eig_topr_kernel(const double* __restrict__ Gin, int N, int R, do
   const double pivmin = 1e-290 * fmax(1.0, maxe2);
   glo -= 2.3e-16 * tnorm * N + pivmin;
   ghi += 2.3e-16 * tnorm * N + pivmin;
-  const int groups = T / kEigProbes;  // eigenvalues worked on at once
-  int* cnts = reinterpret_cast<int*>(part);  // reuse: groups * kEigProbes ints
+  int ppe = 32;  // probes per eigenvalue: largest power of two with (32 / ppe) >= min(R, 32)
+  while (ppe > 1 && 32 / ppe < min(R, 32)) ppe >>= 1;
+  const int groups = 32 / ppe;
+  int rounds = 1;  // (ppe+1)^rounds >= 2^62
+  {
+    double shrink = 1.0;
+    while (shrink < 4.6e18) shrink *= (double)(ppe + 1), ++rounds;
+  }
   for (int r0 = 0; r0 < R; r0 += groups) {
-    const int grp = t / kEigProbes, pr = t % kEigProbes;
+    const int grp = lane / ppe, pr = lane % ppe;
     const int r = r0 + grp;
-    const bool active = grp < groups && r < R;
+    const bool active = r < R;
     const int idx = N - 1 - r;  // ascending index of the r-th largest
     double lo = glo, hi = ghi;
-    for (int round = 0; round < kEigRounds; ++round) {
-      if (active) {
-        double x = lo + (hi - lo) * (double)(pr + 1) / (double)(kEigProbes + 1);
-        cnts[grp * kEigProbes + pr] = sturm_count(d, e, N, x, pivmin);
-      }
-      __syncthreads();
-      if (active) {
-        double nlo = lo, nhi = hi;
-        bool hi_set = false;
-        for (int j = 0; j < kEigProbes; ++j) {
-          double x = lo + (hi - lo) * (double)(j + 1) / (double)(kEigProbes + 1);
-          if (cnts[grp * kEigProbes + j] > idx) {
-            if (!hi_set) nhi = x, hi_set = true;
-          } else {
-            nlo = x;
-          }
-        }
-        lo = nlo, hi = nhi;
-      }
-      __syncthreads();
+    for (int round = 0; round < rounds; ++round) {
+      const double step = (hi - lo) / (double)(ppe + 1);
+      const double x = lo + step * (double)(pr + 1);
+      const int cnt = active ? sturm_count(d, e, N, x, pivmin) : 0;
+      const unsigned ballot = __ballot_sync(0xffffffffu, active && cnt > idx);
+      const unsigned bits = (ppe == 32) ? ballot : ((ballot >> (grp * ppe)) & ((1u << ppe) - 1u));
+      const int f = bits ? (__ffs((int)bits) - 1) : ppe;  // first probe with count > idx
+      const double nlo = (f == 0) ? lo : lo + step * (double)f;
+      const double nhi = (f == ppe) ? hi : lo + step * (double)(f + 1);
+      lo = nlo, hi = nhi;
     }
     if (active && pr == 0) lam[r] = 0.5 * (lo + hi);
   }
-  __syncthreads();
+  __syncwarp();
 
   // ---- 3. eigenvectors of the tridiagonal ---------------------------------------------------------
-  for (int r = t; r < R; r += T)
+  for (int r = lane; r < R; r += 32)
     tridiag_inverse_iteration(d, e, N, lam[r], tnorm, z + (size_t)r * N, lu + (size_t)r * 5 * N, r);
-  __syncthreads();
-  if (t == 0) {  // modified Gram–Schmidt in eigenvalue order (only matters for near-multiple eigenvalues)
+  __syncwarp();
+  if (lane == 0) {  // modified Gram–Schmidt in eigenvalue order (only matters for near-multiple eigenvalues)
     for (int r = 0; r < R; ++r) {
       double* zr = z + (size_t)r * N;
       for (int q = 0; q < r; ++q) {
@@ -278,44 +293,47 @@ __global__ void eig_topr_kernel(const double* __restrict__ Gin, int N, int R, do
       for (int i = 0; i < N; ++i) zr[i] *= nrm;
     }
   }
-  __syncthreads();
+  __syncwarp();
 
-  // ---- 4. back-transform: z <- H_0 H_1 ... H_{N-3} z ----------------------------------------------
-  // 16 lanes per vector; partial dots through `part`, summed in fixed order.
-  for (int r0 = 0; r0 < R; r0 += groups) {
-    const int grp = t / kEigProbes, ln = t % kEigProbes;
-    const int r = r0 + grp;
-    const bool active = grp < groups && r < R;
-    double* zr = z + (size_t)(active ? r : 0) * N;
+  // ---- 4. back-transform: z <- H_0 H_1 ... H_{N-3} z, four vectors at a time ----------------------
+  for (int r0 = 0; r0 < R; r0 += 4) {
+    const int nv = min(4, R - r0);
     for (int k = N - 3; k >= 0; --k) {
       const double tk = tau[k];
-      if (active) {
-        double s = 0.0;
-        for (int i = k + 1 + ln; i < N; i += kEigProbes) s = fma(A[(size_t)i * N + k], zr[i], s);
-        part[grp * kEigProbes + ln] = s;
+      if (tk == 0.0) continue;
+      const double* hk = A + (size_t)k * N;  // reflector k: hk[k+1] = 1, hk[k+2..]
+      double dot[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int i = k + 1 + lane; i < N; i += 32) {
+        const double h = hk[i];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (q < nv) dot[q] = fma(h, z[(size_t)(r0 + q) * N + i], dot[q]);
       }
-      __syncthreads();
-      if (active && tk != 0.0) {
-        double dot = 0.0;
-        for (int j = 0; j < kEigProbes; ++j) dot += part[grp * kEigProbes + j];
-        dot *= tk;
-        for (int i = k + 1 + ln; i < N; i += kEigProbes) zr[i] = fma(-dot, A[(size_t)i * N + k], zr[i]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dot[q] = tk * warp_sum(dot[q]);
+      for (int i = k + 1 + lane; i < N; i += 32) {
+        const double h = hk[i];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (q < nv) z[(size_t)(r0 + q) * N + i] = fma(-dot[q], h, z[(size_t)(r0 + q) * N + i]);
       }
-      __syncthreads();
+      __syncwarp();
     }
   }
+  __syncwarp();
 
   // ---- 5. sign convention and output ------------------------------------------------------------
   // LAPACK returns the Perron pair of a positive matrix with all-negative entries;
   // for every component we pick the sign that makes sum(v) <= 0.  sign_flip overrides per column.
-  for (int r = t; r < R; r += T) {
+  for (int r = 0; r < R; ++r) {
     const double* zr = z + (size_t)r * N;
-    double s = 0.0;
-    for (int i = 0; i < N; ++i) s += zr[i];
+    double part = 0.0;
+    for (int i = lane; i < N; i += 32) part += zr[i];
+    const double s = warp_sum(part);
     double sg = s > 0.0 ? -1.0 : 1.0;
     if (sign_flip) sg *= (double)sign_flip[(size_t)mat * R + r];
-    for (int i = 0; i < N; ++i) evec_out[((size_t)mat * N + i) * R + r] = sg * zr[i];
-    sigma_out[(size_t)mat * R + r] = sqrt(fmax(lam[r], 0.0));
+    for (int i = lane; i < N; i += 32) evec_out[((size_t)mat * N + i) * R + r] = sg * zr[i];
+    if (lane == 0) sigma_out[(size_t)mat * R + r] = sqrt(fmax(lam[r], 0.0));
   }
 }
 

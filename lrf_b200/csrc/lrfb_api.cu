@@ -148,8 +148,8 @@ int make_map(const Geometry& g, int batch, lrfb_qmf_workspace_map* m) {
 // ---- factorisation of one batch of equally shaped matrices ------------------------------------------
 struct FactorWs {  // scratch beyond x/u/v/gram/evec/sigma
   static int gram_split(int n_mat, int M) {
-    int tiles = (M + kGramTileRows - 1) / kGramTileRows;
-    int want = (2 * num_sms() + n_mat - 1) / n_mat;
+    int tiles = (M + kDmmaTileRows - 1) / kDmmaTileRows;
+    int want = (4 * num_sms() + n_mat - 1) / n_mat;
     return std::max(1, std::min(std::min(want, tiles), 32));
   }
   static int64_t bytes(int n_mat, int M, int N, int R) {
@@ -230,7 +230,9 @@ int factorize_batch(const float* x, int n_mat, int M, int N, int R, float lo, fl
       int cnt = std::min(65535, n_mat - m0);
       const float* xx = x + (size_t)m0 * M * N;
       double* go = gout + (size_t)m0 * split * N * N;
-      if (nblocks <= 160) {
+      if (N == 64) {
+        LRFB_LAUNCH(gram64_dmma_kernel, dim3(split, cnt), dim3(128), 0, st, xx, (long long)M * N, M, go, split);
+      } else if (nblocks <= 160) {
         launch_gram<1>(xx, (long long)M * N, M, N, go, split, cnt, ((nblocks + 31) / 32) * 32, nblocks, st);
       } else {
         int threads = std::min(256, (((nblocks + 4) / 5 + 31) / 32) * 32);
@@ -243,11 +245,17 @@ int factorize_batch(const float* x, int n_mat, int M, int N, int R, float lo, fl
         if ((rc = check_launch("gram_reduce_kernel"))) return rc;
       }
     }
-    // top-R eigenpairs
-    const int use_shared = N <= 64;
-    const int threads = std::max(64, std::min(256, ((N + 31) / 32) * 32));
-    LRFB_LAUNCH(eig_topr_kernel, dim3(n_mat), dim3(threads), use_shared ? (size_t)N * N * 8 : 0, st, gram, N, R,
-                eig_scratch, evec, sigma, sign_flip, use_shared);
+    // top-R eigenpairs: one warp per matrix
+    const int use_shared = EigScratch::fits_shared(N, R);
+    const size_t eig_smem = use_shared ? ((size_t)N * N + EigScratch::doubles(N, R)) * 8 : 0;
+#ifndef LRFB_SIM
+    if (eig_smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(eig_topr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eig_smem);
+      if (e != cudaSuccess) return fail((int)e, "eig smem attribute: %s", cudaGetErrorString(e));
+    }
+#endif
+    LRFB_LAUNCH(eig_topr_kernel, dim3(n_mat), dim3(32), eig_smem, st, gram, N, R, eig_scratch, evec, sigma,
+                sign_flip, use_shared);
     if ((rc = check_launch("eig_topr_kernel"))) return rc;
     // u0, v0
     for (int m0 = 0; m0 < n_mat; m0 += 65535) {

@@ -143,6 +143,16 @@ inline T __shfl_down_sync(unsigned, T v, int delta, int width = 32) {
   if ((src & ~(width - 1)) != (lane & ~(width - 1))) src = lane;
   return sim::exchange(v, src);
 }
+inline unsigned __ballot_sync(unsigned, bool pred) {
+  unsigned m = 0;
+  for (int l = 0; l < 32; ++l) {
+    int got = __shfl_sync(0xffffffffu, (int)pred, l);
+    int n = sim::ctx.blk->nthreads - (sim::ctx.lin & ~31);
+    if (l < n && got) m |= 1u << l;
+  }
+  return m;
+}
+inline int __ffs(int v) { return __builtin_ffs(v); }
 inline int __reduce_add_sync(unsigned, int v) {
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
