@@ -118,6 +118,19 @@ int32_t lrfb_factorize(const float* d_x, int32_t n_mat, int32_t M, int32_t N, in
                        const float* d_init_v, const int32_t* d_sign_flip, void* d_workspace,
                        int64_t workspace_bytes, void* stream);
 
+/* Stage-level: only the block-coordinate-descent sweeps (lrf/factorization/qmf.py:207-212 with
+ * CoordinateDescent.forward :149-164) in place on d_u [n_mat][M][R] / d_v [n_mat][N][R], which hold the
+ * initialisation on entry.  Workspace: at least 32768*R*R bytes. */
+int32_t lrfb_bcd(const float* d_x, int32_t n_mat, int32_t M, int32_t N, int32_t R, float bound_lo,
+                 float bound_hi, int32_t num_iters, float* d_u, float* d_v, void* d_workspace,
+                 int64_t workspace_bytes, void* stream);
+
+/* Measurement helpers: number of kernels this library has launched so far (process-wide), and an FP32
+ * FFMA throughput probe (launches num_SMs*8 blocks of 256 threads doing iters*32 dependent-chain FMAs on
+ * 16 chains: flops = num_SMs*8*256*iters*64) used as the FP32 roofline denominator. */
+int64_t lrfb_launch_count(void);
+int32_t lrfb_ffma_probe(float* d_out, int32_t iters, void* stream);
+
 /* Exact per-image sum of squared differences of two uint8 batches (lrf/utils/metrics.py:24-35 before
  * the mean); d_sse [batch] must be zeroed by the caller. psnr = 20*log10(255/sqrt(sse/n)). */
 int32_t lrfb_sse_u8(const uint8_t* d_a, const uint8_t* d_b, int64_t elems_per_image, int32_t batch,

@@ -9,20 +9,26 @@
 
 namespace lrfb {
 
-__global__ void __launch_bounds__(128)
+constexpr int kProjRows = 128;  // rows per CTA tile (= threads per CTA)
+
+// grid = (row tiles, matrices), 128 threads.  The X tile is staged through shared memory with
+// coalesced loads (row stride N+1: conflict-free for the thread-per-row reads that follow).
+__global__ void __launch_bounds__(kProjRows)
 svd_project_kernel(const float* __restrict__ X, long long x_stride, int M, int N, int R,
                    const double* __restrict__ evec, const double* __restrict__ sigma,
                    float* __restrict__ U0, float* __restrict__ V0) {
   LRFB_DYN_SMEM(smem_raw);
-  double* ev = reinterpret_cast<double*>(smem_raw);  // [N][R]
+  double* ev = reinterpret_cast<double*>(smem_raw);               // [N][R]
+  float* xt = reinterpret_cast<float*>(ev + (size_t)N * R);       // [kProjRows][N+1]
   const int mat = blockIdx.y;
   const int keep = min(R, min(M, N));
+  const int XS = N + 1;
   for (int i = threadIdx.x; i < N * R; i += blockDim.x) ev[i] = evec[(size_t)mat * N * R + i];
-  __syncthreads();
   const float* x = X + (size_t)mat * x_stride;
   float* u0 = U0 + (size_t)mat * M * R;
   float* v0 = V0 + (size_t)mat * N * R;
   const double* sg = sigma + (size_t)mat * R;
+  __syncthreads();
   if (blockIdx.x == 0) {
     for (int i = threadIdx.x; i < N * R; i += blockDim.x) {
       int r = i % R;
@@ -31,22 +37,32 @@ svd_project_kernel(const float* __restrict__ X, long long x_stride, int M, int N
       v0[i] = val;
     }
   }
-  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < M; m += gridDim.x * blockDim.x) {
-    for (int r0 = 0; r0 < R; r0 += 4) {
-      double acc[4] = {0.0, 0.0, 0.0, 0.0};
-      for (int k = 0; k < N; ++k) {
-        double xv = (double)x[(size_t)m * N + k];
+  for (int r0 = blockIdx.x * kProjRows; r0 < M; r0 += gridDim.x * kProjRows) {
+    const int valid = min(kProjRows, M - r0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < valid * N; e += blockDim.x) {
+      int r = e / N, c = e - r * N;
+      xt[r * XS + c] = x[(size_t)r0 * N + e];
+    }
+    __syncthreads();
+    const int m = threadIdx.x;
+    if (m < valid) {
+      for (int c0 = 0; c0 < R; c0 += 4) {
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int k = 0; k < N; ++k) {
+          const double xv = (double)xt[m * XS + k];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (r0 + j < R) acc[j] = fma(xv, ev[k * R + r0 + j], acc[j]);
-      }
+          for (int j = 0; j < 4; ++j)
+            if (c0 + j < R) acc[j] = fma(xv, ev[k * R + c0 + j], acc[j]);
+        }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        int r = r0 + j;
-        if (r >= R) break;
-        float val = 0.0f;
-        if (r < keep && sg[r] > 0.0) val = __fmul_rn((float)(acc[j] / sg[r]), __fsqrt_rn((float)sg[r]));
-        u0[(size_t)m * R + r] = val;
+        for (int j = 0; j < 4; ++j) {
+          const int r = c0 + j;
+          if (r >= R) break;
+          float val = 0.0f;
+          if (r < keep && sg[r] > 0.0) val = __fmul_rn((float)(acc[j] / sg[r]), __fsqrt_rn((float)sg[r]));
+          u0[(size_t)(r0 + m) * R + r] = val;
+        }
       }
     }
   }

@@ -6,6 +6,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -24,6 +25,7 @@ using namespace lrfb;
 namespace {
 
 thread_local char g_err[512] = "";
+long long g_launches = 0;  // kernels launched by this library (bench.py reports it as gpu_launches)
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -38,13 +40,17 @@ int dev_copy(void* dst, const void* src, size_t n, cudaStream_t) {
   memcpy(dst, src, n);
   return 0;
 }
-int check_launch(const char*) { return 0; }
+int check_launch(const char*) {
+  ++g_launches;
+  return 0;
+}
 int num_sms() { return 4; }
 #else
 int dev_copy(void* dst, const void* src, size_t n, cudaStream_t st) {
   return (int)cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, st);
 }
 int check_launch(const char* what) {
+  __atomic_fetch_add(&g_launches, 1, __ATOMIC_RELAXED);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail((int)e, "%s: %s", what, cudaGetErrorString(e));
   return 0;
@@ -170,9 +176,9 @@ void launch_gram(const float* x, long long xs, int M, int N, double* out, int sp
   LRFB_LAUNCH(gram_kernel<BPT>, dim3(split, n_mat, gz), dim3(threads), smem, st, x, xs, M, N, out, split);
 }
 
-template <int R>
-int launch_bcd_fast(const BcdBatch& b, cudaStream_t st) {
-  constexpr int N = 64, TM = 128, NT = 64;
+template <int R, int TM, int NT>
+int launch_bcd_cfg(const BcdBatch& b, cudaStream_t st) {
+  constexpr int N = 64;
   auto kern = bcd_kernel<N, R, TM, NT>;
   size_t smem = sizeof(BcdSmem<N, R, TM, NT>);
   int per_sm = 2;
@@ -185,6 +191,18 @@ int launch_bcd_fast(const BcdBatch& b, cudaStream_t st) {
   int grid = std::min(b.n_mat, num_sms() * per_sm);
   LRFB_LAUNCH(kern, dim3(grid), dim3(NT), smem, st, b);
   return check_launch("bcd_kernel");
+}
+
+template <int R>
+int launch_bcd_fast(const BcdBatch& b, cudaStream_t st) {
+  static int variant = -1;  // dev knob: LRFB_BCD_VARIANT=0 (128 rows, 64 thr) | 1 (128, 128) | 2 (64, 64)
+  if (variant < 0) {
+    const char* e = getenv("LRFB_BCD_VARIANT");
+    variant = e ? atoi(e) : 1;
+  }
+  if (variant == 0) return launch_bcd_cfg<R, 128, 64>(b, st);
+  if (variant == 2) return launch_bcd_cfg<R, 64, 64>(b, st);
+  return launch_bcd_cfg<R, 128, 128>(b, st);
 }
 
 int run_bcd(const BcdBatch& b, int N, int R, float* bwork, cudaStream_t st) {
@@ -260,8 +278,15 @@ int factorize_batch(const float* x, int n_mat, int M, int N, int R, float lo, fl
     // u0, v0
     for (int m0 = 0; m0 < n_mat; m0 += 65535) {
       int cnt = std::min(65535, n_mat - m0);
-      int gx = std::max(1, std::min((M + 127) / 128, 64));
-      LRFB_LAUNCH(svd_project_kernel, dim3(gx, cnt), dim3(128), (size_t)N * R * 8, st, x + (size_t)m0 * M * N,
+      int gx = std::max(1, std::min((M + kProjRows - 1) / kProjRows, 256));
+      size_t psmem = (size_t)N * R * 8 + (size_t)kProjRows * (N + 1) * 4;
+#ifndef LRFB_SIM
+      if (psmem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(svd_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
+        if (e != cudaSuccess) return fail((int)e, "project smem attribute: %s", cudaGetErrorString(e));
+      }
+#endif
+      LRFB_LAUNCH(svd_project_kernel, dim3(gx, cnt), dim3(kProjRows), psmem, st, x + (size_t)m0 * M * N,
                   (long long)M * N, M, N, R, evec + (size_t)m0 * N * R, sigma + (size_t)m0 * R,
                   u + (size_t)m0 * M * R, v + (size_t)m0 * N * R);
       if ((rc = check_launch("svd_project_kernel"))) return rc;
@@ -432,6 +457,31 @@ LRFB_EXPORT int32_t lrfb_factorize(const float* d_x, int32_t n_mat, int32_t M, i
   return factorize_batch(d_x, n_mat, M, N, R, bound_lo, bound_hi, num_iters, d_u, d_v, nullptr, nullptr, 0,
                          d_init_u, d_init_v, d_sign_flip, gram, evec, sigma, ws, 0,
                          (cudaStream_t)(uintptr_t)stream);
+}
+
+LRFB_EXPORT int64_t lrfb_launch_count(void) { return g_launches; }
+
+LRFB_EXPORT int32_t lrfb_bcd(const float* d_x, int32_t n_mat, int32_t M, int32_t N, int32_t R, float bound_lo,
+                             float bound_hi, int32_t num_iters, float* d_u, float* d_v, void* d_workspace,
+                             int64_t workspace_bytes, void* stream) {
+  if (!d_x || !d_u || !d_v || n_mat <= 0 || M <= 0 || N <= 0 || R <= 0 || num_iters <= 0)
+    return fail(LRFB_E_ARG, "bad arguments");
+  if (R > kGenMaxR || N > 1024) return fail(LRFB_E_UNSUPPORTED, "N=%d R=%d not implemented", N, R);
+  int rc = check_bounds(bound_lo, bound_hi);
+  if (rc) return rc;
+  if (workspace_bytes < (int64_t)4096 * 2 * R * R * 4 || !d_workspace)
+    return fail(LRFB_E_WORKSPACE, "workspace too small");
+  BcdBatch b;
+  b.X = d_x, b.x_stride = (long long)M * N, b.U = d_u, b.V = d_v, b.Uq = nullptr, b.Vq = nullptr;
+  b.uq_stride = b.vq_stride = 0;
+  b.M = M, b.n_mat = n_mat, b.num_iters = num_iters, b.lo = ceilf(bound_lo), b.hi = floorf(bound_hi);
+  return run_bcd(b, N, R, reinterpret_cast<float*>(d_workspace), (cudaStream_t)(uintptr_t)stream);
+}
+
+LRFB_EXPORT int32_t lrfb_ffma_probe(float* d_out, int32_t iters, void* stream) {
+  if (!d_out || iters <= 0) return fail(LRFB_E_ARG, "bad arguments");
+  LRFB_LAUNCH(ffma_probe_kernel, dim3(num_sms() * 8), dim3(256), 0, (cudaStream_t)(uintptr_t)stream, d_out, iters);
+  return check_launch("ffma_probe_kernel");
 }
 
 LRFB_EXPORT int32_t lrfb_qmf_decode(const lrfb_qmf_config* cfg, int32_t batch, const int8_t* d_factors,

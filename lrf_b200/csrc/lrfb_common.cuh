@@ -58,4 +58,23 @@ __device__ __forceinline__ void cp_async_wait() {
 #endif
 }
 
+// FP32 FFMA throughput probe: 16 independent chains per thread, `iters` x 16 x 2 FMAs each.
+// flops = gridDim.x * blockDim.x * iters * 64;  bench.py times it to get the FP32 roofline denominator.
+__global__ void __launch_bounds__(256) ffma_probe_kernel(float* out, int iters) {
+  float a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = (float)(threadIdx.x + i) * 1e-3f;
+  const float m = 1.0000001f, c = 1e-7f, m2 = 0.9999999f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = __fmaf_rn(a[i], m, c);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = __fmaf_rn(a[i], m2, c);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += a[i];
+  if (s == 12345.678f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace lrfb
