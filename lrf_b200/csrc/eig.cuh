@@ -134,7 +134,8 @@ __device__ inline void tridiag_inverse_iteration(const double* d, const double* 
 __global__ void __launch_bounds__(32)
 eig_topr_kernel(const double* __restrict__ Gin, int N, int R, double* __restrict__ scratch_all,
                 double* __restrict__ evec_out, double* __restrict__ sigma_out,
-                const int* __restrict__ sign_flip, int use_shared) {
+                const int* __restrict__ sign_flip, int use_shared, int M_rows, float* __restrict__ v0_out,
+                float* __restrict__ s0_out) {
   LRFB_DYN_SMEM(smem_raw);
   const int mat = blockIdx.x;
   const int lane = threadIdx.x;
@@ -332,8 +333,16 @@ eig_topr_kernel(const double* __restrict__ Gin, int N, int R, double* __restrict
     const double s = warp_sum(part);
     double sg = s > 0.0 ? -1.0 : 1.0;
     if (sign_flip) sg *= (double)sign_flip[(size_t)mat * R + r];
-    for (int i = lane; i < N; i += 32) evec_out[((size_t)mat * N + i) * R + r] = sg * zr[i];
-    if (lane == 0) sigma_out[(size_t)mat * R + r] = sqrt(fmax(lam[r], 0.0));
+    const double sig = sqrt(fmax(lam[r], 0.0));
+    // SVDInit (lrf/factorization/qmf.py:45-52): keep min(R, M, N) triplets, v0 = V_R * sqrt(s) in f32
+    const bool kept = r < min(M_rows, N) && sig > 0.0;
+    const float s32 = kept ? (float)sig : 0.0f;
+    const float rs = __fsqrt_rn(s32);
+    for (int i = lane; i < N; i += 32) {
+      evec_out[((size_t)mat * N + i) * R + r] = sg * zr[i];
+      v0_out[((size_t)mat * N + i) * R + r] = kept ? __fmul_rn((float)(sg * zr[i]), rs) : 0.0f;
+    }
+    if (lane == 0) sigma_out[(size_t)mat * R + r] = sig, s0_out[(size_t)mat * R + r] = s32;
   }
 }
 

@@ -15,7 +15,6 @@
 #include "eig.cuh"
 #include "frontend.cuh"
 #include "gram.cuh"
-#include "init.cuh"
 #include "lrfb_common.cuh"
 
 using namespace lrfb;
@@ -145,7 +144,7 @@ int make_map(const Geometry& g, int batch, lrfb_qmf_workspace_map* m) {
     m->evec[pl] = off;
     off = align_up(off + (int64_t)batch * L.cols * L.rank[pl] * 8, 256);
     m->sigma[pl] = off;
-    off = align_up(off + (int64_t)batch * L.rank[pl] * 8, 256);
+    off = align_up(off + (int64_t)batch * L.rank[pl] * 12, 256);
   }
   m->total_bytes = off;
   return 0;
@@ -226,6 +225,7 @@ int factorize_batch(const float* x, int n_mat, int M, int N, int R, float lo, fl
                     const float* init_v, const int32_t* sign_flip, double* gram, double* evec, double* sigma,
                     unsigned char* scratch, int stop_after_init, cudaStream_t st) {
   int rc;
+  float* s0 = nullptr;
   const int split = FactorWs::gram_split(n_mat, M);
   double* gram_part = nullptr;
   if (split > 1) {
@@ -272,31 +272,17 @@ int factorize_batch(const float* x, int n_mat, int M, int N, int R, float lo, fl
       if (e != cudaSuccess) return fail((int)e, "eig smem attribute: %s", cudaGetErrorString(e));
     }
 #endif
+    s0 = reinterpret_cast<float*>(sigma + (size_t)n_mat * R);  // f32 singular values behind the f64 ones
     LRFB_LAUNCH(eig_topr_kernel, dim3(n_mat), dim3(32), eig_smem, st, gram, N, R, eig_scratch, evec, sigma,
-                sign_flip, use_shared);
+                sign_flip, use_shared, M, v, s0);
     if ((rc = check_launch("eig_topr_kernel"))) return rc;
-    // u0, v0
-    for (int m0 = 0; m0 < n_mat; m0 += 65535) {
-      int cnt = std::min(65535, n_mat - m0);
-      int gx = std::max(1, std::min((M + kProjRows - 1) / kProjRows, 256));
-      size_t psmem = (size_t)N * R * 8 + (size_t)kProjRows * (N + 1) * 4;
-#ifndef LRFB_SIM
-      if (psmem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(svd_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
-        if (e != cudaSuccess) return fail((int)e, "project smem attribute: %s", cudaGetErrorString(e));
-      }
-#endif
-      LRFB_LAUNCH(svd_project_kernel, dim3(gx, cnt), dim3(kProjRows), psmem, st, x + (size_t)m0 * M * N,
-                  (long long)M * N, M, N, R, evec + (size_t)m0 * N * R, sigma + (size_t)m0 * R,
-                  u + (size_t)m0 * M * R, v + (size_t)m0 * N * R);
-      if ((rc = check_launch("svd_project_kernel"))) return rc;
-    }
   }
   if (stop_after_init) return 0;
   BcdBatch b;
   b.X = x, b.x_stride = (long long)M * N, b.U = u, b.V = v, b.Uq = uq, b.Vq = vq;
   b.uq_stride = b.vq_stride = q_stride;
   b.M = M, b.n_mat = n_mat, b.num_iters = iters, b.lo = ceilf(lo), b.hi = floorf(hi);
+  b.s0 = s0;
   if (iters <= 0) return fail(LRFB_E_UNSUPPORTED, "num_iters must be >= 1");
   return run_bcd(b, N, R, bwork, st);
 }
@@ -433,7 +419,7 @@ LRFB_EXPORT int32_t lrfb_qmf_encode(const lrfb_qmf_config* cfg, int32_t batch, c
 LRFB_EXPORT int64_t lrfb_factorize_workspace_bytes(int32_t n_mat, int32_t M, int32_t N, int32_t R) {
   if (n_mat <= 0 || M <= 0 || N <= 0 || R <= 0) return 0;
   return align_up((int64_t)n_mat * N * N * 8, 256) + align_up((int64_t)n_mat * N * R * 8, 256) +
-         align_up((int64_t)n_mat * R * 8, 256) + FactorWs::bytes(n_mat, M, N, R);
+         align_up((int64_t)n_mat * R * 12, 256) + FactorWs::bytes(n_mat, M, N, R);
 }
 
 LRFB_EXPORT int32_t lrfb_factorize(const float* d_x, int32_t n_mat, int32_t M, int32_t N, int32_t R,
@@ -453,7 +439,7 @@ LRFB_EXPORT int32_t lrfb_factorize(const float* d_x, int32_t n_mat, int32_t M, i
   double* evec = reinterpret_cast<double*>(ws);
   ws += align_up((int64_t)n_mat * N * R * 8, 256);
   double* sigma = reinterpret_cast<double*>(ws);
-  ws += align_up((int64_t)n_mat * R * 8, 256);
+  ws += align_up((int64_t)n_mat * R * 12, 256);
   return factorize_batch(d_x, n_mat, M, N, R, bound_lo, bound_hi, num_iters, d_u, d_v, nullptr, nullptr, 0,
                          d_init_u, d_init_v, d_sign_flip, gram, evec, sigma, ws, 0,
                          (cudaStream_t)(uintptr_t)stream);
@@ -474,6 +460,7 @@ LRFB_EXPORT int32_t lrfb_bcd(const float* d_x, int32_t n_mat, int32_t M, int32_t
   BcdBatch b;
   b.X = d_x, b.x_stride = (long long)M * N, b.U = d_u, b.V = d_v, b.Uq = nullptr, b.Vq = nullptr;
   b.uq_stride = b.vq_stride = 0;
+  b.s0 = nullptr;
   b.M = M, b.n_mat = n_mat, b.num_iters = num_iters, b.lo = ceilf(bound_lo), b.hi = floorf(bound_hi);
   return run_bcd(b, N, R, reinterpret_cast<float*>(d_workspace), (cudaStream_t)(uintptr_t)stream);
 }
