@@ -11,6 +11,7 @@
 #include <algorithm>
 
 #include "bcd.cuh"
+#include "bcd_resident.cuh"
 #include "decode.cuh"
 #include "eig.cuh"
 #include "frontend.cuh"
@@ -204,7 +205,64 @@ int launch_bcd_fast(const BcdBatch& b, cudaStream_t st) {
   return launch_bcd_cfg<R, 128, 128>(b, st);
 }
 
+// shared-memory-resident cluster kernel: N = 64, R <= 4, M <= 8 * 768 rows
+template <int R>
+int launch_bcd_resident(const BcdBatch& b, cudaStream_t st) {
+  constexpr int NT = 384;
+  const int need = (b.M + kResRows - 1) / kResRows;
+  int csize = 1;
+  while (csize < need) csize *= 2;
+  const int rows_per_cta = (b.M + csize - 1) / csize;
+  auto kern = bcd_resident_kernel<R, NT>;
+  const size_t smem = sizeof(ResSmem<R, NT>);
+#ifdef LRFB_SIM
+  LRFB_LAUNCH(kern, dim3(std::min(b.n_mat, 2)), dim3(NT), smem, st, b, 1, rows_per_cta);
+  return check_launch("bcd_resident_kernel");
+#else
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail((int)e, "bcd_resident smem attribute: %s", cudaGetErrorString(e));
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = csize, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(NT), cfg.dynamicSmemBytes = smem, cfg.stream = st, cfg.attrs = attr, cfg.numAttrs = 1;
+  cfg.gridDim = dim3(csize);
+  int max_clusters = 0;
+  e = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
+  if (e != cudaSuccess || max_clusters < 1) {
+    cudaGetLastError();
+    max_clusters = std::max(1, num_sms() / csize);
+  }
+  cfg.gridDim = dim3((unsigned)(std::min(b.n_mat, max_clusters) * csize));
+  e = cudaLaunchKernelEx(&cfg, kern, b, csize, rows_per_cta);
+  if (e != cudaSuccess) return fail((int)e, "bcd_resident launch: %s", cudaGetErrorString(e));
+  return check_launch("bcd_resident_kernel");
+#endif
+}
+
+bool resident_ok(int N, int R, int M) {
+  static int enabled = -1;  // dev knob: LRFB_BCD_RESIDENT=0 forces the streaming kernel
+  if (enabled < 0) {
+    const char* e = getenv("LRFB_BCD_RESIDENT");
+    enabled = e ? atoi(e) : 1;
+  }
+  if (!enabled || N != 64 || R > 4 || bmm_native(N, M, R)) return false;
+#ifdef LRFB_SIM
+  return M <= kResRows;  // the CPU shim has no clusters
+#else
+  return M <= 8 * kResRows;
+#endif
+}
+
 int run_bcd(const BcdBatch& b, int N, int R, float* bwork, cudaStream_t st) {
+  if (resident_ok(N, R, b.M)) {
+    switch (R) {
+      case 1: return launch_bcd_resident<1>(b, st);
+      case 2: return launch_bcd_resident<2>(b, st);
+      case 3: return launch_bcd_resident<3>(b, st);
+      default: return launch_bcd_resident<4>(b, st);
+    }
+  }
   const bool fast = (N == 64 && R <= 4 && !bmm_native(N, b.M, R));
   if (fast) {
     switch (R) {
