@@ -32,8 +32,8 @@ struct ResSmem {
   float b2[R * R];
   float a2[N * R];
   float s0inv[4];
-  double red[(NW / 2) * N * R];   // staged in-CTA reduction, NW/2 warps per round
-  double gred[NW * R * R];
+  float red[NW * N * R];          // per-warp f32 chunk sums of X^T U, summed in f64 in warp order
+  int gred[NW * R * R];
   double part[2][N * R + R * R];  // this CTA's partial S and U^T U, read by the whole cluster
 };
 
@@ -52,7 +52,7 @@ bcd_resident_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
   constexpr int RT = kResRows / NT;  // rows per thread in the A-phase
   constexpr int NG = NT / 16;        // half-warp row groups in the V-phase
   constexpr int NW = NT / 32;
-  static_assert(kResRows % NT == 0 && NW % 2 == 0, "thread shape");
+  static_assert(kResRows % NT == 0, "thread shape");
   using S = ResSmem<R, NT>;
   LRFB_DYN_SMEM(smem_raw);
   S& sm = *reinterpret_cast<S*>(smem_raw);
@@ -163,87 +163,63 @@ bcd_resident_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
       }
       __syncthreads();
 
-      // ---------------- V-phase: S[n][r] += X[m][n] * U[m][r]  (f32 over <=32-row chunks, f64 across) ----
-      double dacc[4][R];
+      // ---------------- V-phase: S[n][r] += X[m][n] * U[m][r] ----------------
+      // f32 within a <=64-row chunk (two half warps of <=32 rows each), chunk sums combined in f64.
       {
-        const int grp = tid >> 4, ln = tid & 15;
+        const int grp = tid >> 4, ln = tid & 15, w = tid >> 5;
+        constexpr int RPG = kResRows / NG;  // rows per half-warp group
+        static_assert(RPG <= 32, "one f32 chunk per group per sweep");
+        float sacc[4][R];
 #pragma unroll
         for (int c = 0; c < 4; ++c)
 #pragma unroll
-          for (int r = 0; r < R; ++r) dacc[c][r] = 0.0;
-        for (int base = grp; base < kResRows; base += NG * 32) {
-          float sacc[4][R];
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-#pragma unroll
-            for (int r = 0; r < R; ++r) sacc[c][r] = 0.0f;
+          for (int r = 0; r < R; ++r) sacc[c][r] = 0.0f;
 #pragma unroll 4
-          for (int q = 0; q < 32; ++q) {
-            const int row = base + q * NG;
-            if (row < kResRows) {
-              const float4 xv = *reinterpret_cast<const float4*>(&sm.x[row * N + ((ln ^ (row & 7)) << 2)]);
-              float u[R];
+        for (int q = 0; q < RPG; ++q) {
+          const int row = grp + q * NG;
+          const float4 xv = *reinterpret_cast<const float4*>(&sm.x[row * N + ((ln ^ (row & 7)) << 2)]);
+          float u[R];
 #pragma unroll
-              for (int r = 0; r < R; ++r) u[r] = sm.u[row * R + r];
+          for (int r = 0; r < R; ++r) u[r] = sm.u[row * R + r];
 #pragma unroll
-              for (int r = 0; r < R; ++r) {
-                sacc[0][r] = __fmaf_rn(xv.x, u[r], sacc[0][r]);
-                sacc[1][r] = __fmaf_rn(xv.y, u[r], sacc[1][r]);
-                sacc[2][r] = __fmaf_rn(xv.z, u[r], sacc[2][r]);
-                sacc[3][r] = __fmaf_rn(xv.w, u[r], sacc[3][r]);
-              }
-            }
+          for (int r = 0; r < R; ++r) {
+            sacc[0][r] = __fmaf_rn(xv.x, u[r], sacc[0][r]);
+            sacc[1][r] = __fmaf_rn(xv.y, u[r], sacc[1][r]);
+            sacc[2][r] = __fmaf_rn(xv.z, u[r], sacc[2][r]);
+            sacc[3][r] = __fmaf_rn(xv.w, u[r], sacc[3][r]);
           }
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-#pragma unroll
-            for (int r = 0; r < R; ++r) dacc[c][r] += (double)sacc[c][r];
         }
-        // the two half warps of a warp
 #pragma unroll
         for (int c = 0; c < 4; ++c)
 #pragma unroll
-          for (int r = 0; r < R; ++r) dacc[c][r] += __shfl_xor_sync(0xffffffffu, dacc[c][r], 16);
-      }
-      // U^T U partial of this warp (exact integers carried as doubles)
-      {
+          for (int r = 0; r < R; ++r) sacc[c][r] = __fadd_rn(sacc[c][r], __shfl_xor_sync(0xffffffffu, sacc[c][r], 16));
+        if ((tid & 31) < 16) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int r = 0; r < R; ++r) sm.red[(w * N + ln * 4 + c) * R + r] = sacc[c][r];
+        }
+        // U^T U partial of this warp: exact integers, one REDUX per entry
         int idx = 0;
 #pragma unroll
         for (int j = 0; j < R; ++j)
 #pragma unroll
           for (int r = j; r < R; ++r) {
-            double g = (double)gacc[idx++];
-            for (int o = 16; o; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
-            if ((tid & 31) == 0) {
-              sm.gred[(tid >> 5) * R * R + j * R + r] = g;
-              sm.gred[(tid >> 5) * R * R + r * R + j] = g;
-            }
+            const int g = __reduce_add_sync(0xffffffffu, gacc[idx++]);
+            if ((tid & 31) == 0) sm.gred[w * R * R + j * R + r] = g, sm.gred[w * R * R + r * R + j] = g;
           }
       }
-      // staged cross-warp reduction in fixed warp order: two rounds of NW/2 warps
-      double tot = 0.0;
-      for (int round = 0; round < 2; ++round) {
-        const int w = (tid >> 5) - round * (NW / 2);
-        if (w >= 0 && w < NW / 2 && (tid & 31) < 16) {
-          const int ln = tid & 15;
+      __syncthreads();
+      if (tid < N * R) {  // fixed warp order, f64
+        double tot = 0.0;
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
+        for (int w2 = 0; w2 < NW; ++w2) tot += (double)sm.red[w2 * N * R + tid];
+        sm.part[pbuf][tid] = tot;
+      } else if (tid < N * R + R * R) {
+        int g = 0;
 #pragma unroll
-            for (int r = 0; r < R; ++r) sm.red[(w * N + ln * 4 + c) * R + r] = dacc[c][r];
-        }
-        __syncthreads();
-        if (tid < N * R) {
-#pragma unroll
-          for (int w2 = 0; w2 < NW / 2; ++w2) tot += sm.red[w2 * N * R + tid];
-        }
-        __syncthreads();
-      }
-      if (tid < N * R) sm.part[pbuf][tid] = tot;
-      if (tid < R * R) {
-        double g = 0.0;
-#pragma unroll
-        for (int w2 = 0; w2 < NW; ++w2) g += sm.gred[w2 * R * R + tid];
-        sm.part[pbuf][N * R + tid] = g;
+        for (int w2 = 0; w2 < NW; ++w2) g += sm.gred[w2 * R * R + tid - N * R];
+        sm.part[pbuf][tid] = (double)g;
       }
 
       // ---------------- exchange partials across the cluster, every CTA sums in rank order ----------------
@@ -278,7 +254,17 @@ bcd_resident_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
         for (int r = 0; r < R; ++r) sm.v[n * R + r] = f[r];
       }
       __syncthreads();
-      gram_small<N, R>(sm.v, sm.b, tid);
+      // B = V^T V: V is integer-valued now, every order gives the same exact f32 result
+      {
+        const int w = tid >> 5, lane = tid & 31;
+        for (int e = w; e < R * R; e += NW) {
+          const int j = e / R, r = e - j * R;
+          float p = __fmaf_rn(sm.v[lane * R + j], sm.v[lane * R + r],
+                              __fmul_rn(sm.v[(lane + 32) * R + j], sm.v[(lane + 32) * R + r]));
+          for (int o = 16; o; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+          if (lane == 0) sm.b[e] = p;
+        }
+      }
       __syncthreads();
     }
 

@@ -206,9 +206,8 @@ int launch_bcd_fast(const BcdBatch& b, cudaStream_t st) {
 }
 
 // shared-memory-resident cluster kernel: N = 64, R <= 4, M <= 8 * 768 rows
-template <int R>
-int launch_bcd_resident(const BcdBatch& b, cudaStream_t st) {
-  constexpr int NT = 384;
+template <int R, int NT>
+int launch_bcd_resident_nt(const BcdBatch& b, cudaStream_t st) {
   const int need = (b.M + kResRows - 1) / kResRows;
   int csize = 1;
   while (csize < need) csize *= 2;
@@ -238,6 +237,11 @@ int launch_bcd_resident(const BcdBatch& b, cudaStream_t st) {
   if (e != cudaSuccess) return fail((int)e, "bcd_resident launch: %s", cudaGetErrorString(e));
   return check_launch("bcd_resident_kernel");
 #endif
+}
+
+template <int R>
+int launch_bcd_resident(const BcdBatch& b, cudaStream_t st) {
+  return launch_bcd_resident_nt<R, 384>(b, st);
 }
 
 bool resident_ok(int N, int R, int M) {
