@@ -22,7 +22,7 @@ struct EigScratch {  // per matrix (doubles): d, e, tau, vv, w [5N] | lam [32] |
   static __host__ __device__ size_t doubles(int N, int R) {
     return (size_t)5 * N + kEigMaxR + (size_t)R * N + (size_t)R * 5 * N + 8;
   }
-  static __host__ __device__ bool fits_shared(int N, int R) { return N <= 64 && R <= 4; }
+  static __host__ __device__ bool fits_shared(int N, int R) { return N == 64 && R <= 4; }
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -39,6 +39,7 @@ __device__ inline int sturm_count(const double* d, const double* e, int N, doubl
   double p = d[0] - x;
   if (fabs(p) < pivmin) p = -pivmin;
   int cnt = p < 0.0;
+#pragma unroll 2
   for (int i = 1; i < N; ++i) {
     double pn = fma(d[i] - x, p, -(e[i - 1] * e[i - 1]) * pm);
     if (fabs(pn) < pivmin * fabs(p)) pn = -pivmin * p;
@@ -61,12 +62,14 @@ __device__ inline void tridiag_inverse_iteration(const double* d, const double* 
   double* du2 = lu + 3 * N;
   double* piv = lu + 4 * N;
   const double tol = fmax(tnorm, 1e-300) * 2.3e-16;
+#pragma unroll 1
   for (int i = 0; i < N; ++i) {
     dd[i] = d[i] - lam;
     dl[i] = du[i] = (i < N - 1) ? e[i] : 0.0;
     du2[i] = 0.0;
     piv[i] = 0.0;
   }
+#pragma unroll 1
   for (int i = 0; i < N - 1; ++i) {
     if (fabs(dd[i]) >= fabs(dl[i])) {
       if (fabs(dd[i]) < tol) dd[i] = (dd[i] < 0.0) ? -tol : tol;
@@ -94,11 +97,15 @@ __device__ inline void tridiag_inverse_iteration(const double* d, const double* 
   dd[N - 1] = 1.0 / dd[N - 1];
 
   unsigned s = 12345u + 7919u * (unsigned)seed;
+#pragma unroll 1
   for (int i = 0; i < N; ++i) {  // deterministic start vector with no special structure
     s = s * 1664525u + 1013904223u;
     z[i] = 0.5 + (double)(s >> 8) * (1.0 / 16777216.0);
   }
+#pragma unroll 1
+#pragma unroll 1
   for (int it = 0; it < 3; ++it) {
+#pragma unroll 1
     for (int i = 0; i < N - 1; ++i) {
       if (piv[i] == 0.0) {
         z[i + 1] -= dl[i] * z[i];
@@ -110,19 +117,24 @@ __device__ inline void tridiag_inverse_iteration(const double* d, const double* 
     }
     z[N - 1] *= dd[N - 1];
     if (N > 1) z[N - 2] = (z[N - 2] - du[N - 2] * z[N - 1]) * dd[N - 2];
+#pragma unroll 1
     for (int i = N - 3; i >= 0; --i) z[i] = (z[i] - du[i] * z[i + 1] - du2[i] * z[i + 2]) * dd[i];
     double mx = 0.0;
+#pragma unroll 1
     for (int i = 0; i < N; ++i) mx = fmax(mx, fabs(z[i]));
     if (!(mx > 0.0) || !(mx < 1e300)) {  // breakdown guard: restart from a basis vector
+#pragma unroll 1
       for (int i = 0; i < N; ++i) z[i] = (i == seed % N) ? 1.0 : 0.0;
       mx = 1.0;
     }
     double inv = 1.0 / mx, nrm = 0.0;
+#pragma unroll 1
     for (int i = 0; i < N; ++i) {
       z[i] *= inv;
       nrm = fma(z[i], z[i], nrm);
     }
     nrm = 1.0 / sqrt(nrm);
+#pragma unroll 1
     for (int i = 0; i < N; ++i) z[i] *= nrm;
   }
 }
@@ -131,19 +143,24 @@ __device__ inline void tridiag_inverse_iteration(const double* d, const double* 
 // working copy stays in global memory).  Outputs per matrix: evec[N][R] (unit, sign-fixed, row-major)
 // and sigma[R] = sqrt(max(lambda, 0)).  sign_flip: optional [n][R] of +1/-1 multiplied onto the
 // convention (test hook, may be null).
+// NC > 0: N is the compile-time constant NC and everything lives in shared memory (LDS/STS with 32-bit
+// addressing); NC == 0: run-time N, working set in global memory.
+template <int NC>
 __global__ void __launch_bounds__(32)
-eig_topr_kernel(const double* __restrict__ Gin, int N, int R, double* __restrict__ scratch_all,
+eig_topr_kernel(const double* __restrict__ Gin, int Nrt, int R, double* __restrict__ scratch_all,
                 double* __restrict__ evec_out, double* __restrict__ sigma_out,
                 const int* __restrict__ sign_flip, int use_shared, int M_rows, float* __restrict__ v0_out,
                 float* __restrict__ s0_out) {
   LRFB_DYN_SMEM(smem_raw);
+  const int N = NC ? NC : Nrt;
   const int mat = blockIdx.x;
   const int lane = threadIdx.x;
   double* A;
   double* scratch;
-  if (use_shared) {
+  (void)use_shared;
+  if (NC) {
     A = reinterpret_cast<double*>(smem_raw);
-    scratch = A + (size_t)N * N;
+    scratch = A + N * N;
     const double* g = Gin + (size_t)mat * N * N;
     for (int i = lane; i < N * N; i += 32) A[i] = g[i];
   } else {
@@ -161,8 +178,9 @@ eig_topr_kernel(const double* __restrict__ Gin, int N, int R, double* __restrict
   __syncwarp();
 
   // ---- 1. tridiagonalisation -------------------------------------------------------------------
+#pragma unroll 1
   for (int k = 0; k < N - 2; ++k) {
-    const double* rowk = A + (size_t)k * N;  // x = A[k][k+1..] (= column k by symmetry)
+    const double* rowk = A + k * N;  // x = A[k][k+1..] (= column k by symmetry)
     const double alpha0 = rowk[k + 1];
     double part = 0.0;
     for (int c = k + 2 + lane; c < N; c += 32) part = fma(rowk[c], rowk[c], part);
@@ -183,14 +201,17 @@ eig_topr_kernel(const double* __restrict__ Gin, int N, int R, double* __restrict
       // p = tau * A22 v, kept in w[] for now
       double kpart = 0.0;
       for (int c = k + 1 + lane; c < N; c += 32) {
-        double s0 = 0.0, s1 = 0.0;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
         int j = k + 1;
-        for (; j + 1 < N; j += 2) {
-          s0 = fma(A[(size_t)j * N + c], vv[j], s0);
-          s1 = fma(A[(size_t)(j + 1) * N + c], vv[j + 1], s1);
+#pragma unroll 2
+        for (; j + 3 < N; j += 4) {
+          s0 = fma(A[(j + 0) * N + c], vv[j + 0], s0);
+          s1 = fma(A[(j + 1) * N + c], vv[j + 1], s1);
+          s2 = fma(A[(j + 2) * N + c], vv[j + 2], s2);
+          s3 = fma(A[(j + 3) * N + c], vv[j + 3], s3);
         }
-        if (j < N) s0 = fma(A[(size_t)j * N + c], vv[j], s0);
-        const double pc = tk * (s0 + s1);
+        for (; j < N; ++j) s0 = fma(A[j * N + c], vv[j], s0);
+        const double pc = tk * ((s0 + s1) + (s2 + s3));
         w[c] = pc;
         kpart = fma(pc, vv[c], kpart);
       }
@@ -199,25 +220,26 @@ eig_topr_kernel(const double* __restrict__ Gin, int N, int R, double* __restrict
       __syncwarp();
       for (int c = k + 1 + lane; c < N; c += 32) {  // A22 -= v w^T + w v^T
         const double vc = vv[c], wc = w[c];
+#pragma unroll 4
         for (int j = k + 1; j < N; ++j) {
-          double a = A[(size_t)j * N + c];
+          double a = A[j * N + c];
           a = fma(-vv[j], wc, a);
           a = fma(-w[j], vc, a);
-          A[(size_t)j * N + c] = a;
+          A[j * N + c] = a;
         }
       }
     }
     __syncwarp();
-    for (int c = k + 1 + lane; c < N; c += 32) A[(size_t)k * N + c] = vv[c];  // keep reflector k in row k
+    for (int c = k + 1 + lane; c < N; c += 32) A[k * N + c] = vv[c];  // keep reflector k in row k
     __syncwarp();
   }
   if (lane == 0) {
     if (N >= 2) {
-      d[N - 2] = A[(size_t)(N - 2) * N + (N - 2)];
-      e[N - 2] = A[(size_t)(N - 2) * N + (N - 1)];
+      d[N - 2] = A[(N - 2) * N + (N - 2)];
+      e[N - 2] = A[(N - 2) * N + (N - 1)];
       tau[N - 2] = 0.0;
     }
-    d[N - 1] = A[(size_t)(N - 1) * N + (N - 1)];
+    d[N - 1] = A[(N - 1) * N + (N - 1)];
     e[N - 1] = 0.0;
     tau[N - 1] = 0.0;
   }
@@ -225,6 +247,7 @@ eig_topr_kernel(const double* __restrict__ Gin, int N, int R, double* __restrict
 
   // ---- 2. R largest eigenvalues by multisection ------------------------------------------------
   double glo = d[0], ghi = d[0], maxe2 = 0.0;
+#pragma unroll 1
   for (int i = 0; i < N; ++i) {  // Gershgorin bounds, redundantly per lane
     double r = (i > 0 ? fabs(e[i - 1]) : 0.0) + (i < N - 1 ? fabs(e[i]) : 0.0);
     glo = fmin(glo, d[i] - r);
@@ -238,10 +261,10 @@ eig_topr_kernel(const double* __restrict__ Gin, int N, int R, double* __restrict
   int ppe = 32;  // probes per eigenvalue: largest power of two with (32 / ppe) >= min(R, 32)
   while (ppe > 1 && 32 / ppe < min(R, 32)) ppe >>= 1;
   const int groups = 32 / ppe;
-  int rounds = 1;  // (ppe+1)^rounds >= 2^62
-  {
+  int rounds = 1;  // (ppe+1)^rounds >= 2^46: eigenvalues to ~1e-14 of ||T|| (sigma is rounded to f32,
+  {                 // and inverse iteration only needs the shift to be much closer than the gaps)
     double shrink = 1.0;
-    while (shrink < 4.6e18) shrink *= (double)(ppe + 1), ++rounds;
+    while (shrink < 7.0e13) shrink *= (double)(ppe + 1), ++rounds;
   }
   for (int r0 = 0; r0 < R; r0 += groups) {
     const int grp = lane / ppe, pr = lane % ppe;
@@ -249,6 +272,7 @@ eig_topr_kernel(const double* __restrict__ Gin, int N, int R, double* __restrict
     const bool active = r < R;
     const int idx = N - 1 - r;  // ascending index of the r-th largest
     double lo = glo, hi = ghi;
+#pragma unroll 1
     for (int round = 0; round < rounds; ++round) {
       const double step = (hi - lo) / (double)(ppe + 1);
       const double x = lo + step * (double)(pr + 1);
@@ -266,31 +290,38 @@ eig_topr_kernel(const double* __restrict__ Gin, int N, int R, double* __restrict
 
   // ---- 3. eigenvectors of the tridiagonal ---------------------------------------------------------
   for (int r = lane; r < R; r += 32)
-    tridiag_inverse_iteration(d, e, N, lam[r], tnorm, z + (size_t)r * N, lu + (size_t)r * 5 * N, r);
+    tridiag_inverse_iteration(d, e, N, lam[r], tnorm, z + r * N, lu + r * 5 * N, r);
   __syncwarp();
   if (lane == 0) {  // modified Gram–Schmidt in eigenvalue order (only matters for near-multiple eigenvalues)
     for (int r = 0; r < R; ++r) {
-      double* zr = z + (size_t)r * N;
+      double* zr = z + r * N;
       for (int q = 0; q < r; ++q) {
-        const double* zq = z + (size_t)q * N;
+        const double* zq = z + q * N;
         double dot = 0.0;
+#pragma unroll 1
         for (int i = 0; i < N; ++i) dot = fma(zr[i], zq[i], dot);
+#pragma unroll 1
         for (int i = 0; i < N; ++i) zr[i] = fma(-dot, zq[i], zr[i]);
       }
       double nrm = 0.0;
+#pragma unroll 1
       for (int i = 0; i < N; ++i) nrm = fma(zr[i], zr[i], nrm);
       if (nrm < 1e-20) {  // degenerate (rank-deficient input): fall back to a basis vector
+#pragma unroll 1
         for (int i = 0; i < N; ++i) zr[i] = (i == (r % N)) ? 1.0 : 0.0;
         for (int q = 0; q < r; ++q) {
-          const double* zq = z + (size_t)q * N;
+          const double* zq = z + q * N;
           double dot = zq[r % N];
+#pragma unroll 1
           for (int i = 0; i < N; ++i) zr[i] = fma(-dot, zq[i], zr[i]);
         }
         nrm = 0.0;
+#pragma unroll 1
         for (int i = 0; i < N; ++i) nrm = fma(zr[i], zr[i], nrm);
         if (nrm < 1e-20) nrm = 1.0;
       }
       nrm = 1.0 / sqrt(nrm);
+#pragma unroll 1
       for (int i = 0; i < N; ++i) zr[i] *= nrm;
     }
   }
@@ -299,16 +330,17 @@ eig_topr_kernel(const double* __restrict__ Gin, int N, int R, double* __restrict
   // ---- 4. back-transform: z <- H_0 H_1 ... H_{N-3} z, four vectors at a time ----------------------
   for (int r0 = 0; r0 < R; r0 += 4) {
     const int nv = min(4, R - r0);
+#pragma unroll 1
     for (int k = N - 3; k >= 0; --k) {
       const double tk = tau[k];
       if (tk == 0.0) continue;
-      const double* hk = A + (size_t)k * N;  // reflector k: hk[k+1] = 1, hk[k+2..]
+      const double* hk = A + k * N;  // reflector k: hk[k+1] = 1, hk[k+2..]
       double dot[4] = {0.0, 0.0, 0.0, 0.0};
       for (int i = k + 1 + lane; i < N; i += 32) {
         const double h = hk[i];
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          if (q < nv) dot[q] = fma(h, z[(size_t)(r0 + q) * N + i], dot[q]);
+          if (q < nv) dot[q] = fma(h, z[(r0 + q) * N + i], dot[q]);
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) dot[q] = tk * warp_sum(dot[q]);
@@ -316,7 +348,7 @@ eig_topr_kernel(const double* __restrict__ Gin, int N, int R, double* __restrict
         const double h = hk[i];
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          if (q < nv) z[(size_t)(r0 + q) * N + i] = fma(-dot[q], h, z[(size_t)(r0 + q) * N + i]);
+          if (q < nv) z[(r0 + q) * N + i] = fma(-dot[q], h, z[(r0 + q) * N + i]);
       }
       __syncwarp();
     }
@@ -327,7 +359,7 @@ eig_topr_kernel(const double* __restrict__ Gin, int N, int R, double* __restrict
   // LAPACK returns the Perron pair of a positive matrix with all-negative entries;
   // for every component we pick the sign that makes sum(v) <= 0.  sign_flip overrides per column.
   for (int r = 0; r < R; ++r) {
-    const double* zr = z + (size_t)r * N;
+    const double* zr = z + r * N;
     double part = 0.0;
     for (int i = lane; i < N; i += 32) part += zr[i];
     const double s = warp_sum(part);

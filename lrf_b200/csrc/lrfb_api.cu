@@ -330,13 +330,17 @@ int factorize_batch(const float* x, int n_mat, int M, int N, int R, float lo, fl
     const size_t eig_smem = use_shared ? ((size_t)N * N + EigScratch::doubles(N, R)) * 8 : 0;
 #ifndef LRFB_SIM
     if (eig_smem > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(eig_topr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eig_smem);
+      cudaError_t e = cudaFuncSetAttribute(eig_topr_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eig_smem);
       if (e != cudaSuccess) return fail((int)e, "eig smem attribute: %s", cudaGetErrorString(e));
     }
 #endif
     s0 = reinterpret_cast<float*>(sigma + (size_t)n_mat * R);  // f32 singular values behind the f64 ones
-    LRFB_LAUNCH(eig_topr_kernel, dim3(n_mat), dim3(32), eig_smem, st, gram, N, R, eig_scratch, evec, sigma,
-                sign_flip, use_shared, M, v, s0);
+    if (use_shared)
+      LRFB_LAUNCH(eig_topr_kernel<64>, dim3(n_mat), dim3(32), eig_smem, st, gram, N, R, eig_scratch, evec, sigma,
+                  sign_flip, use_shared, M, v, s0);
+    else
+      LRFB_LAUNCH(eig_topr_kernel<0>, dim3(n_mat), dim3(32), 0, st, gram, N, R, eig_scratch, evec, sigma,
+                  sign_flip, use_shared, M, v, s0);
     if ((rc = check_launch("eig_topr_kernel"))) return rc;
   }
   if (stop_after_init) return 0;
