@@ -318,12 +318,10 @@ def main():
     blobs = list(compression._pool().map(lambda i: packing.pack_qmf_record(host[i], lay, meta), range(n_s)))
     pack_s = time.perf_counter() - t0
     bpp = torch.tensor([len(b) * 8 / (H * W) for b in blobs], dtype=torch.float32, device=dev)
+    from lrf_b200.sharding import gather_stats
+
     stats = torch.stack([bpp, psnr[:n_s]], dim=1)
-    if world > 1:
-        gathered = [torch.empty_like(stats) for _ in range(world)]
-        dist.all_gather(gathered, stats)  # the only collective: B/G x 2 floats per rank
-        stats = torch.cat(gathered)
-    stats = stats.cpu()
+    stats = gather_stats(stats, n_s * world, rank, world).cpu()  # the only collective (NCCL all_gather)
 
     if rank == 0:
         line = {
