@@ -19,14 +19,17 @@
 
 namespace lrfb {
 
-constexpr int kResRows = 768;  // rows of X resident per CTA
 
-template <int R, int NT>
+// U rows are kept as bf16 (exact for the integer range [-128, 127]; f32 <-> bf16 is a 16-bit shift).
+__device__ __forceinline__ unsigned short bf16_of(float f) { return (unsigned short)(__float_as_uint(f) >> 16); }
+__device__ __forceinline__ float bf16_to(unsigned short h) { return __uint_as_float((unsigned)h << 16); }
+
+template <int R, int ROWS, int NT>
 struct ResSmem {
   static constexpr int N = 64;
   static constexpr int NW = NT / 32;
-  float x[kResRows * N];          // swizzled
-  float u[kResRows * R];          // current U rows of this CTA
+  float x[ROWS * N];              // swizzled
+  unsigned short u[ROWS * R];     // current U rows of this CTA (bf16)
   float v[N * R];
   float b[R * R];
   float b2[R * R];
@@ -45,15 +48,16 @@ __device__ __forceinline__ void cluster_barrier() {
 #endif
 }
 
-template <int R, int NT>
-__global__ void __launch_bounds__(NT, 1)
+template <int R, int ROWS, int NT>
+__global__ void __launch_bounds__(NT, (ROWS <= 384 ? 2 : 1))
 bcd_resident_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
   constexpr int N = 64;
+  constexpr int kResRows = ROWS;
   constexpr int RT = kResRows / NT;  // rows per thread in the A-phase
   constexpr int NG = NT / 16;        // half-warp row groups in the V-phase
   constexpr int NW = NT / 32;
   static_assert(kResRows % NT == 0, "thread shape");
-  using S = ResSmem<R, NT>;
+  using S = ResSmem<R, ROWS, NT>;
   LRFB_DYN_SMEM(smem_raw);
   S& sm = *reinterpret_cast<S*>(smem_raw);
   const int tid = threadIdx.x;
@@ -95,10 +99,7 @@ bcd_resident_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
       }
       sm.s0inv[tid] = inv;
     }
-    if (!from_a) {
-      const float* U = P.U + (size_t)mat * M * R + (size_t)row0 * R;
-      for (int i = tid; i < kResRows * R; i += NT) sm.u[i] = i < rows_here * R ? U[i] : 0.0f;
-    }
+    const float* Uinit = P.U + (size_t)mat * M * R + (size_t)row0 * R;  // read in sweep 1 only when injected
     cp_async_wait<0>();
     __syncthreads();
     gram_small<N, R>(sm.v, sm.b, tid);
@@ -141,17 +142,22 @@ bcd_resident_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
         for (int i = 0; i < RT; ++i) {
           const int row = tid + i * NT;
           float f[R];
-          if (from_a && it == 0) {
+          const bool ok = row < rows_here;
+          if (it == 0) {
+            if (from_a) {
 #pragma unroll
-            for (int r = 0; r < R; ++r) f[r] = sm.s0inv[r] == 0.0f ? 0.0f : __fmul_rn(acc[i][r], sm.s0inv[r]);
+              for (int r = 0; r < R; ++r) f[r] = sm.s0inv[r] == 0.0f ? 0.0f : __fmul_rn(acc[i][r], sm.s0inv[r]);
+            } else {
+#pragma unroll
+              for (int r = 0; r < R; ++r) f[r] = ok ? Uinit[row * R + r] : 0.0f;
+            }
           } else {
 #pragma unroll
-            for (int r = 0; r < R; ++r) f[r] = sm.u[row * R + r];
+            for (int r = 0; r < R; ++r) f[r] = bf16_to(sm.u[row * R + r]);
           }
           gs_row<R>(f, acc[i], sm.b, t2_native_u, P.lo, P.hi);
-          const bool ok = row < rows_here;
 #pragma unroll
-          for (int r = 0; r < R; ++r) sm.u[row * R + r] = ok ? f[r] : 0.0f;
+          for (int r = 0; r < R; ++r) sm.u[row * R + r] = bf16_of(ok ? f[r] : 0.0f);
           if (ok) {
             int idx = 0;
 #pragma unroll
@@ -179,8 +185,17 @@ bcd_resident_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
           const int row = grp + q * NG;
           const float4 xv = *reinterpret_cast<const float4*>(&sm.x[row * N + ((ln ^ (row & 7)) << 2)]);
           float u[R];
+          if (R == 4) {
+            const uint2 w2 = *reinterpret_cast<const uint2*>(&sm.u[row * 4]);
+            u[0] = __uint_as_float(w2.x << 16), u[1 % R] = __uint_as_float(w2.x & 0xffff0000u);
+            u[2 % R] = __uint_as_float(w2.y << 16), u[3 % R] = __uint_as_float(w2.y & 0xffff0000u);
+          } else if (R == 2) {
+            const unsigned w1 = *reinterpret_cast<const unsigned*>(&sm.u[row * 2]);
+            u[0] = __uint_as_float(w1 << 16), u[1 % R] = __uint_as_float(w1 & 0xffff0000u);
+          } else {
 #pragma unroll
-          for (int r = 0; r < R; ++r) u[r] = sm.u[row * R + r];
+            for (int r = 0; r < R; ++r) u[r] = bf16_to(sm.u[row * R + r]);
+          }
 #pragma unroll
           for (int r = 0; r < R; ++r) {
             sacc[0][r] = __fmaf_rn(xv.x, u[r], sacc[0][r]);
@@ -210,36 +225,40 @@ bcd_resident_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
           }
       }
       __syncthreads();
-      if (tid < N * R) {  // fixed warp order, f64
-        double tot = 0.0;
+      for (int e = tid; e < N * R + R * R; e += NT) {  // fixed warp order, f64
+        if (e < N * R) {
+          double tot = 0.0;
 #pragma unroll
-        for (int w2 = 0; w2 < NW; ++w2) tot += (double)sm.red[w2 * N * R + tid];
-        sm.part[pbuf][tid] = tot;
-      } else if (tid < N * R + R * R) {
-        int g = 0;
+          for (int w2 = 0; w2 < NW; ++w2) tot += (double)sm.red[w2 * N * R + e];
+          sm.part[pbuf][e] = tot;
+        } else {
+          int g = 0;
 #pragma unroll
-        for (int w2 = 0; w2 < NW; ++w2) g += sm.gred[w2 * R * R + tid - N * R];
-        sm.part[pbuf][tid] = (double)g;
+          for (int w2 = 0; w2 < NW; ++w2) g += sm.gred[w2 * R * R + e - N * R];
+          sm.part[pbuf][e] = (double)g;
+        }
       }
 
       // ---------------- exchange partials across the cluster, every CTA sums in rank order ----------------
       if (cluster_size > 1) {
         cluster_barrier();
 #ifndef LRFB_SIM
-        if (tid < N * R + R * R) {
+        for (int e = tid; e < N * R + R * R; e += NT) {
           double s = 0.0;
           for (int cr = 0; cr < cluster_size; ++cr) {
             const double* remote = cluster.map_shared_rank(&sm.part[pbuf][0], cr);
-            s += remote[tid];
+            s += remote[e];
           }
-          if (tid < N * R) sm.a2[tid] = (float)s;
-          else sm.b2[tid - N * R] = (float)s;
+          if (e < N * R) sm.a2[e] = (float)s;
+          else sm.b2[e - N * R] = (float)s;
         }
 #endif
       } else {
         __syncthreads();
-        if (tid < N * R) sm.a2[tid] = (float)sm.part[pbuf][tid];
-        else if (tid < N * R + R * R) sm.b2[tid - N * R] = (float)sm.part[pbuf][tid];
+        for (int e = tid; e < N * R + R * R; e += NT) {
+          if (e < N * R) sm.a2[e] = (float)sm.part[pbuf][e];
+          else sm.b2[e - N * R] = (float)sm.part[pbuf][e];
+        }
       }
       pbuf ^= 1;
       __syncthreads();
@@ -271,7 +290,7 @@ bcd_resident_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
     // ---- write the factors of this CTA's rows (and V once per cluster) ----
     for (int i = tid; i < rows_here * R; i += NT) {
       const int row = i / R, r = i - row * R;
-      const float val = sm.u[i];
+      const float val = bf16_to(sm.u[i]);
       if (P.U) P.U[(size_t)mat * M * R + (size_t)(row0 + row) * R + r] = val;
       if (P.Uq) P.Uq[(size_t)mat * P.uq_stride + (size_t)r * M + row0 + row] = (int8_t)(int)val;
     }

@@ -205,21 +205,28 @@ int launch_bcd_fast(const BcdBatch& b, cudaStream_t st) {
   return launch_bcd_cfg<R, 128, 128>(b, st);
 }
 
-// shared-memory-resident cluster kernel: N = 64, R <= 4, M <= 8 * 768 rows
-template <int R, int NT>
-int launch_bcd_resident_nt(const BcdBatch& b, cudaStream_t st) {
-  const int need = (b.M + kResRows - 1) / kResRows;
+// shared-memory-resident cluster kernel: N = 64, R <= 4.  Two shapes: 384 rows x 192 threads per CTA with
+// 2 CTAs per SM and clusters of up to 16 (default: the serial per-sweep tail of one cluster overlaps the
+// compute of the other), or 768 rows x 384 threads with 1 CTA per SM and clusters of up to 8.
+template <int R, int ROWS, int NT, int MAXC>
+int launch_bcd_resident_cfg(const BcdBatch& b, cudaStream_t st) {
+  const int need = (b.M + ROWS - 1) / ROWS;
   int csize = 1;
   while (csize < need) csize *= 2;
   const int rows_per_cta = (b.M + csize - 1) / csize;
-  auto kern = bcd_resident_kernel<R, NT>;
-  const size_t smem = sizeof(ResSmem<R, NT>);
+  auto kern = bcd_resident_kernel<R, ROWS, NT>;
+  const size_t smem = sizeof(ResSmem<R, ROWS, NT>);
 #ifdef LRFB_SIM
+  (void)MAXC;
   LRFB_LAUNCH(kern, dim3(std::min(b.n_mat, 2)), dim3(NT), smem, st, b, 1, rows_per_cta);
   return check_launch("bcd_resident_kernel");
 #else
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail((int)e, "bcd_resident smem attribute: %s", cudaGetErrorString(e));
+  if (csize > 8) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return fail((int)e, "non-portable cluster size: %s", cudaGetErrorString(e));
+  }
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -230,18 +237,31 @@ int launch_bcd_resident_nt(const BcdBatch& b, cudaStream_t st) {
   e = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
   if (e != cudaSuccess || max_clusters < 1) {
     cudaGetLastError();
-    max_clusters = std::max(1, num_sms() / csize);
+    max_clusters = std::max(1, num_sms() * (ROWS <= 384 ? 2 : 1) / csize);
   }
   cfg.gridDim = dim3((unsigned)(std::min(b.n_mat, max_clusters) * csize));
+  if (getenv("LRFB_DEBUG"))
+    fprintf(stderr, "[lrfb] bcd_resident R=%d rows/cta=%d threads=%d cluster=%d max_active_clusters=%d grid=%u smem=%zu\n",
+            R, ROWS, NT, csize, max_clusters, cfg.gridDim.x, smem);
   e = cudaLaunchKernelEx(&cfg, kern, b, csize, rows_per_cta);
   if (e != cudaSuccess) return fail((int)e, "bcd_resident launch: %s", cudaGetErrorString(e));
   return check_launch("bcd_resident_kernel");
 #endif
 }
 
+int resident_variant() {
+  static int v = -1;  // dev knob: LRFB_RES_VARIANT=0 (768 rows, 1 CTA/SM) | 1 (384 rows, 2 CTAs/SM)
+  if (v < 0) {
+    const char* e = getenv("LRFB_RES_VARIANT");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
 template <int R>
 int launch_bcd_resident(const BcdBatch& b, cudaStream_t st) {
-  return launch_bcd_resident_nt<R, 384>(b, st);
+  if (resident_variant() == 0) return launch_bcd_resident_cfg<R, 768, 384, 8>(b, st);
+  return launch_bcd_resident_cfg<R, 384, 192, 16>(b, st);
 }
 
 bool resident_ok(int N, int R, int M) {
@@ -252,9 +272,9 @@ bool resident_ok(int N, int R, int M) {
   }
   if (!enabled || N != 64 || R > 4 || bmm_native(N, M, R)) return false;
 #ifdef LRFB_SIM
-  return M <= kResRows;  // the CPU shim has no clusters
+  return M <= (resident_variant() == 0 ? 768 : 384);  // the CPU shim has no clusters
 #else
-  return M <= 8 * kResRows;
+  return M <= (resident_variant() == 0 ? 8 * 768 : 16 * 384);
 #endif
 }
 
@@ -285,9 +305,11 @@ int run_bcd(const BcdBatch& b, int N, int R, float* bwork, cudaStream_t st) {
 int factorize_batch(const float* x, int n_mat, int M, int N, int R, float lo, float hi, int iters, float* u,
                     float* v, int8_t* uq, int8_t* vq, long long q_stride, const float* init_u,
                     const float* init_v, const int32_t* sign_flip, double* gram, double* evec, double* sigma,
-                    unsigned char* scratch, int stop_after_init, cudaStream_t st) {
+                    unsigned char* scratch, int stop_after_init, cudaStream_t st, int phase = 0) {
+  // phase 0: init + sweeps, 1: init only, 2: sweeps only (after a phase-1 call with the same arguments)
   int rc;
-  float* s0 = nullptr;
+  const bool injected = init_u && init_v;
+  float* s0 = injected ? nullptr : reinterpret_cast<float*>(sigma + (size_t)n_mat * R);
   const int split = FactorWs::gram_split(n_mat, M);
   double* gram_part = nullptr;
   if (split > 1) {
@@ -298,7 +320,9 @@ int factorize_batch(const float* x, int n_mat, int M, int N, int R, float lo, fl
   scratch += align_up((int64_t)n_mat * (int64_t)EigScratch::doubles(N, R) * 8, 256);
   float* bwork = reinterpret_cast<float*>(scratch);
 
-  if (init_u && init_v) {
+  if (phase == 2) {
+    // nothing to initialise
+  } else if (injected) {
     if ((rc = dev_copy(u, init_u, (size_t)n_mat * M * R * 4, st))) return fail(rc, "copy init u");
     if ((rc = dev_copy(v, init_v, (size_t)n_mat * N * R * 4, st))) return fail(rc, "copy init v");
   } else {
@@ -334,7 +358,7 @@ int factorize_batch(const float* x, int n_mat, int M, int N, int R, float lo, fl
       if (e != cudaSuccess) return fail((int)e, "eig smem attribute: %s", cudaGetErrorString(e));
     }
 #endif
-    s0 = reinterpret_cast<float*>(sigma + (size_t)n_mat * R);  // f32 singular values behind the f64 ones
+    // s0: f32 singular values stored behind the f64 ones
     if (use_shared)
       LRFB_LAUNCH(eig_topr_kernel<64>, dim3(n_mat), dim3(32), eig_smem, st, gram, N, R, eig_scratch, evec, sigma,
                   sign_flip, use_shared, M, v, s0);
@@ -343,7 +367,7 @@ int factorize_batch(const float* x, int n_mat, int M, int N, int R, float lo, fl
                   sign_flip, use_shared, M, v, s0);
     if ((rc = check_launch("eig_topr_kernel"))) return rc;
   }
-  if (stop_after_init) return 0;
+  if (stop_after_init || phase == 1) return 0;
   BcdBatch b;
   b.X = x, b.x_stride = (long long)M * N, b.U = u, b.V = v, b.Uq = uq, b.Vq = vq;
   b.uq_stride = b.vq_stride = q_stride;
@@ -352,6 +376,26 @@ int factorize_batch(const float* x, int n_mat, int M, int N, int R, float lo, fl
   if (iters <= 0) return fail(LRFB_E_UNSUPPORTED, "num_iters must be >= 1");
   return run_bcd(b, N, R, bwork, st);
 }
+
+#ifndef LRFB_SIM
+// Helper stream per device so the chroma sweeps can fill the SMs the luma clusters leave idle.
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+SideStream* side_stream() {
+  static SideStream table[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  SideStream& s = table[dev];
+  if (!s.stream) {
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming);
+  }
+  return &s;
+}
+#endif
 
 int64_t encode_scratch_bytes(const Geometry& g, int batch) {
   int64_t mx = 0;
@@ -468,17 +512,40 @@ LRFB_EXPORT int32_t lrfb_qmf_encode(const lrfb_qmf_config* cfg, int32_t batch, c
   if ((rc = run_frontend(cfg, g, batch, d_images, xs, st))) return rc;
   if (dbg && dbg->stop_after == 1) return 0;
   const lrfb_qmf_layout& L = g.lay;
-  for (int pl = 0; pl < L.n_planes; ++pl) {
-    rc = factorize_batch(xs[pl], batch, L.rows[pl], L.cols, L.rank[pl], cfg->bound_lo, cfg->bound_hi,
-                         cfg->num_iters, reinterpret_cast<float*>(ws + m.u[pl]),
-                         reinterpret_cast<float*>(ws + m.v[pl]), d_factors + L.u_offset[pl],
-                         d_factors + L.v_offset[pl], L.record_bytes, dbg ? dbg->d_init_u[pl] : nullptr,
-                         dbg ? dbg->d_init_v[pl] : nullptr, dbg ? dbg->d_sign_flip[pl] : nullptr,
-                         reinterpret_cast<double*>(ws + m.gram[pl]), reinterpret_cast<double*>(ws + m.evec[pl]),
-                         reinterpret_cast<double*>(ws + m.sigma[pl]), ws + m.total_bytes,
-                         dbg && dbg->stop_after == 2, st);
-    if (rc) return rc;
+  auto run_plane = [&](int pl, int phase, cudaStream_t s) {
+    return factorize_batch(xs[pl], batch, L.rows[pl], L.cols, L.rank[pl], cfg->bound_lo, cfg->bound_hi,
+                           cfg->num_iters, reinterpret_cast<float*>(ws + m.u[pl]),
+                           reinterpret_cast<float*>(ws + m.v[pl]), d_factors + L.u_offset[pl],
+                           d_factors + L.v_offset[pl], L.record_bytes, dbg ? dbg->d_init_u[pl] : nullptr,
+                           dbg ? dbg->d_init_v[pl] : nullptr, dbg ? dbg->d_sign_flip[pl] : nullptr,
+                           reinterpret_cast<double*>(ws + m.gram[pl]), reinterpret_cast<double*>(ws + m.evec[pl]),
+                           reinterpret_cast<double*>(ws + m.sigma[pl]), ws + m.total_bytes,
+                           dbg && dbg->stop_after == 2, s, phase);
+  };
+  // The planes are independent.  When every plane runs the shared-memory-resident sweeps (no shared scratch),
+  // all initialisations run first and the chroma sweeps go to a helper stream: the luma kernel occupies
+  // 15 clusters x 8 SMs, the chroma clusters fill the remaining SMs and take over as luma clusters retire.
+  bool overlap = false;
+#ifndef LRFB_SIM
+  overlap = L.n_planes == 3 && !(dbg && dbg->stop_after == 2) && cfg->num_iters > 0 && !getenv("LRFB_NO_OVERLAP");
+  for (int pl = 0; pl < L.n_planes && overlap; ++pl) overlap = resident_ok(L.cols, L.rank[pl], L.rows[pl]);
+  SideStream* side = overlap ? side_stream() : nullptr;
+  overlap = overlap && side;
+  if (overlap) {
+    for (int pl = 0; pl < 3; ++pl)
+      if ((rc = run_plane(pl, 1, st))) return rc;
+    cudaEventRecord(side->fork, st);
+    cudaStreamWaitEvent(side->stream, side->fork, 0);
+    if ((rc = run_plane(0, 2, st))) return rc;
+    if ((rc = run_plane(1, 2, side->stream))) return rc;
+    if ((rc = run_plane(2, 2, side->stream))) return rc;
+    cudaEventRecord(side->join, side->stream);
+    cudaStreamWaitEvent(st, side->join, 0);
+    return 0;
   }
+#endif
+  for (int pl = 0; pl < L.n_planes; ++pl)
+    if ((rc = run_plane(pl, 0, st))) return rc;
   return 0;
 }
 

@@ -176,6 +176,8 @@ inline float __frcp_rn(float a) { volatile float r = 1.0f / a; return r; }
 inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
 inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
 inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
+inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
+inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
 inline float __int2float_rn(int a) { return (float)a; }
 inline float __uint2float_rn(unsigned a) { return (float)a; }
 inline int __float2int_rz(float a) { return (int)a; }
