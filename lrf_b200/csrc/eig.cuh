@@ -378,4 +378,218 @@ eig_topr_kernel(const double* __restrict__ Gin, int Nrt, int R, double* __restri
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// N = 64 fast path: 64 threads (2 warps) per matrix, thread c keeps COLUMN c of the symmetric matrix in
+// registers (64 doubles) for the whole tridiagonalisation — the rank-2 update and the matrix-vector
+// product are pure DFMA streams with the Householder vector broadcast from shared memory, so the
+// kernel is bound by the FP64 pipe, not by shared-memory capacity (one matrix needs ~16 KB instead of
+// 48 KB: many more matrices in flight).  Reflector k is written to row k of the (dead) Gram buffer in
+// global memory and read back, coalesced, for the back-transformation.  Phases 2-5 as in the generic
+// kernel, with the multisection split across the two warps.
+// ---------------------------------------------------------------------------------------------------
+struct Eig64Smem {
+  double xs[64], vv[64], w[64], d[64], e[64], tau[64];
+  double red[4];
+  double lam[4];
+  double z[4 * 64];
+  double lu[4 * 5 * 64];
+};
+
+__device__ __forceinline__ double block64_sum(double v, double* red, int tid) {  // 2 warps; every thread gets the sum
+  v = warp_sum(v);
+  if ((tid & 31) == 0) red[tid >> 5] = v;
+  __syncthreads();
+  const double s = red[0] + red[1];
+  __syncthreads();
+  return s;
+}
+
+__global__ void __launch_bounds__(64)
+eig64_topr_kernel(double* __restrict__ G, int R, double* __restrict__ evec_out, double* __restrict__ sigma_out,
+                  const int* __restrict__ sign_flip, int M_rows, float* __restrict__ v0_out,
+                  float* __restrict__ s0_out) {
+  constexpr int N = 64;
+  __shared__ Eig64Smem sm;
+  const int mat = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* g = G + (size_t)mat * N * N;
+  double a[N];  // column `tid`
+#pragma unroll
+  for (int j = 0; j < N; ++j) a[j] = g[j * N + tid];
+
+  // ---- 1. tridiagonalisation ----
+#pragma unroll 1
+  for (int k = 0; k < N - 2; ++k) {
+    if (warp == (k >> 5)) {
+      if (tid == k) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) sm.xs[j] = a[j];  // column k = row k (symmetric): x and the diagonal
+      }
+    }
+    __syncthreads();
+    const double alpha0 = sm.xs[k + 1];
+    const double xc = sm.xs[tid];
+    const double xn2 = block64_sum(tid >= k + 2 ? xc * xc : 0.0, sm.red, tid);
+    double beta, tk, scal;
+    if (xn2 == 0.0) {
+      beta = alpha0, tk = 0.0, scal = 0.0;
+    } else {
+      const double nrm = sqrt(fma(alpha0, alpha0, xn2));
+      beta = alpha0 >= 0.0 ? -nrm : nrm;
+      tk = (beta - alpha0) / beta;
+      scal = 1.0 / (alpha0 - beta);
+    }
+    const double vc = tid == k + 1 ? 1.0 : (tid > k + 1 ? xc * scal : 0.0);
+    sm.vv[tid] = vc;
+    g[k * N + tid] = vc;  // reflector k (coalesced); row k of G is dead
+    if (tid == 0) sm.d[k] = sm.xs[k], sm.e[k] = beta, sm.tau[k] = tk;
+    __syncthreads();
+    if (tk != 0.0) {  // uniform
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+      for (int j = 0; j < N; j += 4) {
+        s0 = fma(a[j + 0], sm.vv[j + 0], s0);
+        s1 = fma(a[j + 1], sm.vv[j + 1], s1);
+        s2 = fma(a[j + 2], sm.vv[j + 2], s2);
+        s3 = fma(a[j + 3], sm.vv[j + 3], s3);
+      }
+      const double pc = tid > k ? tk * ((s0 + s1) + (s2 + s3)) : 0.0;
+      const double kk = 0.5 * tk * block64_sum(pc * vc, sm.red, tid);
+      const double wc = tid > k ? fma(-kk, vc, pc) : 0.0;
+      sm.w[tid] = wc;
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        double t = fma(-sm.vv[j], wc, a[j]);
+        a[j] = fma(-sm.w[j], vc, t);
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == N - 2) sm.d[N - 2] = a[N - 2], sm.e[N - 2] = a[N - 1], sm.tau[N - 2] = 0.0;
+  if (tid == N - 1) sm.d[N - 1] = a[N - 1], sm.e[N - 1] = 0.0, sm.tau[N - 1] = 0.0;
+  __syncthreads();
+
+  // ---- 2. R largest eigenvalues: each warp multisects its share of the eigenvalues ----
+  const double* d = sm.d;
+  const double* e = sm.e;
+  double glo = d[0], ghi = d[0], maxe2 = 0.0;
+#pragma unroll 1
+  for (int i = 0; i < N; ++i) {
+    double r = (i > 0 ? fabs(e[i - 1]) : 0.0) + (i < N - 1 ? fabs(e[i]) : 0.0);
+    glo = fmin(glo, d[i] - r);
+    ghi = fmax(ghi, d[i] + r);
+    maxe2 = fmax(maxe2, e[i] * e[i]);
+  }
+  const double tnorm = fmax(fabs(glo), fabs(ghi));
+  const double pivmin = 1e-290 * fmax(1.0, maxe2);
+  glo -= 2.3e-16 * tnorm * N + pivmin;
+  ghi += 2.3e-16 * tnorm * N + pivmin;
+  {
+    const int per_warp = (R + 1) / 2;  // eigenvalues handled by each warp
+    int ppe = 32;
+    while (ppe > 1 && 32 / ppe < per_warp) ppe >>= 1;
+    int rounds = 1;
+    {
+      double shrink = 1.0;
+      while (shrink < 7.0e13) shrink *= (double)(ppe + 1), ++rounds;
+    }
+    const int grp = lane / ppe, pr = lane % ppe;
+    const int r = warp * per_warp + grp;
+    const bool active = grp < per_warp && r < R;
+    const int idx = N - 1 - r;
+    double lo = glo, hi = ghi;
+#pragma unroll 1
+    for (int round = 0; round < rounds; ++round) {
+      const double step = (hi - lo) / (double)(ppe + 1);
+      const double x = lo + step * (double)(pr + 1);
+      const int cnt = active ? sturm_count(d, e, N, x, pivmin) : 0;
+      const unsigned ballot = __ballot_sync(0xffffffffu, active && cnt > idx);
+      const unsigned bits = (ppe == 32) ? ballot : ((ballot >> (grp * ppe)) & ((1u << ppe) - 1u));
+      const int f = bits ? (__ffs((int)bits) - 1) : ppe;
+      const double nlo = (f == 0) ? lo : lo + step * (double)f;
+      const double nhi = (f == ppe) ? hi : lo + step * (double)(f + 1);
+      lo = nlo, hi = nhi;
+    }
+    if (active && pr == 0) sm.lam[r] = 0.5 * (lo + hi);
+  }
+  __syncthreads();
+
+  // ---- 3. eigenvectors of the tridiagonal (one thread each), MGS by thread 0 ----
+  if (tid < R) tridiag_inverse_iteration(d, e, N, sm.lam[tid], tnorm, sm.z + tid * N, sm.lu + tid * 5 * N, tid);
+  __syncthreads();
+  if (tid == 0) {
+    for (int r = 0; r < R; ++r) {
+      double* zr = sm.z + r * N;
+      for (int q = 0; q < r; ++q) {
+        const double* zq = sm.z + q * N;
+        double dot = 0.0;
+#pragma unroll 1
+        for (int i = 0; i < N; ++i) dot = fma(zr[i], zq[i], dot);
+#pragma unroll 1
+        for (int i = 0; i < N; ++i) zr[i] = fma(-dot, zq[i], zr[i]);
+      }
+      double nrm = 0.0;
+#pragma unroll 1
+      for (int i = 0; i < N; ++i) nrm = fma(zr[i], zr[i], nrm);
+      if (nrm < 1e-20) {  // degenerate input: fall back to a basis vector
+#pragma unroll 1
+        for (int i = 0; i < N; ++i) zr[i] = (i == r) ? 1.0 : 0.0;
+        for (int q = 0; q < r; ++q) {
+          const double* zq = sm.z + q * N;
+          const double dot = zq[r];
+#pragma unroll 1
+          for (int i = 0; i < N; ++i) zr[i] = fma(-dot, zq[i], zr[i]);
+        }
+        nrm = 0.0;
+#pragma unroll 1
+        for (int i = 0; i < N; ++i) nrm = fma(zr[i], zr[i], nrm);
+        if (nrm < 1e-20) nrm = 1.0;
+      }
+      nrm = 1.0 / sqrt(nrm);
+#pragma unroll 1
+      for (int i = 0; i < N; ++i) zr[i] *= nrm;
+    }
+  }
+  __syncthreads();
+
+  // ---- 4. back-transform: thread c holds element c of each vector and column c of the reflectors ----
+  double zc[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) zc[q] = q < R ? sm.z[q * N + tid] : 0.0;
+#pragma unroll
+  for (int k = 0; k < N - 2; ++k) a[k] = g[k * N + tid];  // reflector k, element `tid` (written by this thread)
+#pragma unroll
+  for (int k = N - 3; k >= 0; --k) {
+    const double tk = sm.tau[k];
+    const double h = tid > k ? a[k] : 0.0;
+    double dot[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dot[q] = warp_sum(h * zc[q]);
+    if (lane == 0) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) sm.xs[warp * 4 + q] = dot[q];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) zc[q] = fma(-tk * (sm.xs[q] + sm.xs[4 + q]), h, zc[q]);
+    __syncthreads();
+  }
+
+  // ---- 5. sign convention (sum(v) <= 0, see eig_topr_kernel) and output ----
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    if (r >= R) break;
+    const double s = block64_sum(zc[r], sm.red, tid);
+    double sg = s > 0.0 ? -1.0 : 1.0;
+    if (sign_flip) sg *= (double)sign_flip[(size_t)mat * R + r];
+    const double sig = sqrt(fmax(sm.lam[r], 0.0));
+    const bool kept = r < min(M_rows, N) && sig > 0.0;
+    const float s32 = kept ? (float)sig : 0.0f;
+    const float rs = __fsqrt_rn(s32);
+    evec_out[((size_t)mat * N + tid) * R + r] = sg * zc[r];
+    v0_out[((size_t)mat * N + tid) * R + r] = kept ? __fmul_rn((float)(sg * zc[r]), rs) : 0.0f;
+    if (tid == 0) sigma_out[(size_t)mat * R + r] = sig, s0_out[(size_t)mat * R + r] = s32;
+  }
+}
+
 }  // namespace lrfb

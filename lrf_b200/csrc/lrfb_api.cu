@@ -359,7 +359,18 @@ int factorize_batch(const float* x, int n_mat, int M, int N, int R, float lo, fl
     }
 #endif
     // s0: f32 singular values stored behind the f64 ones
-    if (use_shared)
+    static int eig_v3 = -1;  // dev knob: LRFB_EIG_V3=0 selects the one-warp shared-memory kernel
+    if (eig_v3 < 0) {
+      const char* ev = getenv("LRFB_EIG_V3");
+#ifdef LRFB_SIM
+      eig_v3 = ev ? atoi(ev) : 0;  // the 2-warp kernel is barrier-heavy: minutes per matrix on the CPU shim
+#else
+      eig_v3 = ev ? atoi(ev) : 1;
+#endif
+    }
+    if (use_shared && eig_v3)
+      LRFB_LAUNCH(eig64_topr_kernel, dim3(n_mat), dim3(64), 0, st, gram, R, evec, sigma, sign_flip, M, v, s0);
+    else if (use_shared)
       LRFB_LAUNCH(eig_topr_kernel<64>, dim3(n_mat), dim3(32), eig_smem, st, gram, N, R, eig_scratch, evec, sigma,
                   sign_flip, use_shared, M, v, s0);
     else
