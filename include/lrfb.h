@@ -131,6 +131,19 @@ int32_t lrfb_bcd(const float* d_x, int32_t n_mat, int32_t M, int32_t N, int32_t 
 int64_t lrfb_launch_count(void);
 int32_t lrfb_ffma_probe(float* d_out, int32_t iters, void* stream);
 
+/* SVD baseline codec, color_space RGB + patch (replaces lrf/compression/svd.py:156-187: pad_image, patchify,
+ * torch.linalg.svd, top-R, *sqrt(s), quantize(u), quantize(v)).  cfg->color_space = LRFB_RGB, cfg->rank[0] = R
+ * (bounds / num_iters unused).  d_codes: [batch][record_bytes] uint8 in the lrfb_qmf_layout record layout
+ * (U then V, fiber-major); d_qparams: [batch][4] f32 = {scale_u, min_u, scale_v, min_v} — the values the
+ * reference stores under metadata["quantization"].  Workspace: lrfb_qmf_workspace_query. */
+int32_t lrfb_svd_encode(const lrfb_qmf_config* cfg, int32_t batch, const void* d_images, uint8_t* d_codes,
+                        float* d_qparams, void* d_workspace, int64_t workspace_bytes, const lrfb_qmf_debug* dbg,
+                        void* stream);
+/* Replaces lrf.svd_decode after un-packing (svd.py:316-359): dequantize, u @ v.T, depatchify, unpad, to uint8.
+ * d_qparams6: [batch][6] f32 = {scale_u, min_u, scale_v, min_v, min code of u, min code of v}. */
+int32_t lrfb_svd_decode(const lrfb_qmf_config* cfg, int32_t batch, const uint8_t* d_codes, const float* d_qparams6,
+                        uint8_t* d_images, void* stream);
+
 /* Exact per-image sum of squared differences of two uint8 batches (lrf/utils/metrics.py:24-35 before
  * the mean); d_sse [batch] must be zeroed by the caller. psnr = 20*log10(255/sqrt(sse/n)). */
 int32_t lrfb_sse_u8(const uint8_t* d_a, const uint8_t* d_b, int64_t elems_per_image, int32_t batch,

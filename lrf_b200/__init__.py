@@ -6,13 +6,13 @@ the built library and a CUDA device (no CPU fallback).
 """
 from .compression import (  # noqa: F401
     qmf_encode, qmf_decode, qmf_encode_batch, qmf_decode_batch, qmf_rank, resolve_plan, EncodePlan,
-    decode_records, sse_u8, psnr_batch,
+    decode_records, sse_u8, psnr_batch, svd_encode, svd_decode, svd_encode_batch,
 )
 from .factorization import QMF  # noqa: F401
 from .metrics import psnr, mse, bits_per_pixel, compression_ratio, get_memory_usage  # noqa: F401
 from .packing import combine_bytes, separate_bytes, dict_to_bytes, bytes_to_dict  # noqa: F401
 
 __all__ = [
-    "qmf_encode", "qmf_decode", "qmf_encode_batch", "qmf_decode_batch", "qmf_rank", "QMF", "psnr", "mse",
+    "qmf_encode", "qmf_decode", "svd_encode", "svd_decode", "qmf_encode_batch", "qmf_decode_batch", "qmf_rank", "QMF", "psnr", "mse",
     "bits_per_pixel", "compression_ratio", "combine_bytes", "separate_bytes",
 ]

@@ -73,6 +73,9 @@ PROTOTYPES = {
                              C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "lrfb_launch_count": (C.c_int64, []),
     "lrfb_ffma_probe": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "lrfb_svd_encode": (C.c_int32, [C.POINTER(QmfConfig), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_int64, C.POINTER(QmfDebug), C.c_void_p]),
+    "lrfb_svd_decode": (C.c_int32, [C.POINTER(QmfConfig), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "lrfb_sse_u8": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "lrfb_ctx_create": (C.c_int32, [C.c_int32, C.POINTER(C.c_void_p)]),
     "lrfb_ctx_destroy": (None, [C.c_void_p]),

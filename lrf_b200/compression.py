@@ -273,3 +273,103 @@ def psnr_batch(a: torch.Tensor, b: torch.Tensor, max_value: float = 255.0) -> to
     """lrf/utils/metrics.py:57-71 per image, from the exact integer SSE."""
     mse = sse_u8(a, b).double() / a[0].numel()
     return 20 * torch.log10(max_value / torch.sqrt(mse))
+
+
+# ----------------------------------------------------------------------------------------------------
+# SVD baseline codec (lrf/compression/svd.py), color_space="RGB", patch=True — the only branch of the
+# reference that round-trips (SURVEY §3.3: its YCbCr branch appends "padded size" twice and fails to decode).
+# ----------------------------------------------------------------------------------------------------
+
+
+def _svd_plan(H, W, rank, quality, patch_size):
+    probe = _cabi.make_config(H, W, patch_size, "RGB", _cabi.LRFB_U8, (0.5, 0.5), (1,), (-1, 1), 1)
+    lay = _cabi.QmfLayout()
+    _cabi.check(_cabi.lib().lrfb_qmf_layout_query(C.byref(probe), C.byref(lay)), "lrfb_qmf_layout_query")
+    if rank is None:
+        assert quality >= 0 and quality <= 100, "'quality' must be between 0 and 100."
+        R = max(round(min(lay.rows[0], lay.cols) * quality / 100), 1)  # compression/svd.py:173-177
+    else:
+        R = rank
+    cfg = _cabi.make_config(H, W, patch_size, "RGB", _cabi.LRFB_U8, (0.5, 0.5), (R,), (-1, 1), 1)
+    _cabi.check(_cabi.lib().lrfb_qmf_layout_query(C.byref(cfg), C.byref(lay)), "lrfb_qmf_layout_query")
+    return cfg, lay
+
+
+def svd_encode_batch(images: torch.Tensor, rank=None, quality=None, color_space: str = "RGB",
+                     scale_factor=(0.5, 0.5), patch: bool = True, patch_size=(8, 8), dtype=None,
+                     sign_flip: Optional[torch.Tensor] = None, return_records: bool = False):
+    """Batched ``svd_encode``: uint8 images (B,3,H,W) → list of encoded ``bytes``."""
+    assert (rank, quality) != (None, None), "Either 'rank' or 'quality' must be specified."
+    if color_space != "RGB" or not patch:
+        raise NotImplementedError("lrf_b200: svd codec implements color_space='RGB', patch=True only")
+    if images.dtype != torch.uint8 or (dtype is not None and dtype != torch.uint8):
+        raise NotImplementedError("lrf_b200: svd codec implements uint8 images / uint8 factors only")
+    _require_cuda()
+    device = images.device if images.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    B, _, H, W = images.shape
+    cfg, lay = _svd_plan(H, W, rank, quality, patch_size)
+    with torch.cuda.device(device):
+        dev_images = images.to(device).contiguous()
+        m = _cabi.QmfWorkspaceMap()
+        _cabi.check(_cabi.lib().lrfb_qmf_workspace_query(C.byref(cfg), B, C.byref(m)), "lrfb_qmf_workspace_query")
+        ws = torch.empty(m.total_bytes, dtype=torch.uint8, device=device)
+        codes = torch.empty((B, lay.record_bytes), dtype=torch.uint8, device=device)
+        qparams = torch.empty((B, 4), dtype=torch.float32, device=device)
+        dbg = _cabi.QmfDebug()
+        if sign_flip is not None:
+            sf = sign_flip.to(device=device, dtype=torch.int32).contiguous()
+            dbg.d_sign_flip[0] = sf.data_ptr()
+        rc = _cabi.lib().lrfb_svd_encode(C.byref(cfg), B, C.c_void_p(dev_images.data_ptr()),
+                                         C.c_void_p(codes.data_ptr()), C.c_void_p(qparams.data_ptr()),
+                                         C.c_void_p(ws.data_ptr()), m.total_bytes, C.byref(dbg), _stream_ptr())
+        _cabi.check(rc, "lrfb_svd_encode")
+        if return_records:
+            return codes, qparams, cfg, lay
+        host, qp = codes.cpu().numpy(), qparams.cpu()
+    out = []
+    for i in range(B):
+        meta = {"dtype": "uint8", "color space": "RGB", "patch": True, "patch size": patch_size,
+                "original size": [lay.orig_h[0], lay.orig_w[0]], "padded size": [lay.pad_h[0], lay.pad_w[0]],
+                "quantization": {"u": [qp[i, 0].item(), qp[i, 1].item()], "v": [qp[i, 2].item(), qp[i, 3].item()]}}
+        r, mm, n = lay.rank[0], lay.rows[0], lay.cols
+        u = host[i, lay.u_offset[0] : lay.u_offset[0] + r * mm].reshape(r, mm)
+        v = host[i, lay.v_offset[0] : lay.v_offset[0] + r * n].reshape(r, n)
+        out.append(packing.combine_bytes([packing.dict_to_bytes(meta),
+                                          packing.combine_bytes([packing.encode_fibers(u, "uint8"),
+                                                                 packing.encode_fibers(v, "uint8")])]))
+    return out
+
+
+def svd_encode(image: torch.Tensor, rank=None, quality=None, color_space: str = "RGB", scale_factor=(0.5, 0.5),
+               patch: bool = True, patch_size=(8, 8), dtype=None) -> bytes:
+    """Drop-in for ``lrf.svd_encode`` (lrf/compression/svd.py:117-294), RGB + patch branch."""
+    return svd_encode_batch(image.unsqueeze(0), rank, quality, color_space, scale_factor, patch, patch_size,
+                            dtype)[0]
+
+
+def svd_decode(encoded_image: bytes) -> torch.Tensor:
+    """Drop-in for ``lrf.svd_decode`` (lrf/compression/svd.py:297-361), RGB + patch streams → CPU uint8."""
+    _require_cuda()
+    meta_b, body = packing.separate_bytes(encoded_image, 2)
+    meta = packing.bytes_to_dict(meta_b)
+    if meta["color space"] != "RGB" or not meta["patch"] or meta["dtype"] != "uint8" or meta["quantization"]["u"] is None:
+        raise NotImplementedError("lrf_b200: svd_decode implements uint8 RGB patch streams only")
+    u, v = (packing.decode_fibers(b) for b in packing.separate_bytes(body, 2))
+    H, W = meta["original size"]
+    cfg = _cabi.make_config(H, W, meta["patch size"], "RGB", _cabi.LRFB_U8, (0.5, 0.5), (u.shape[0],), (-1, 1), 1)
+    lay = _cabi.QmfLayout()
+    _cabi.check(_cabi.lib().lrfb_qmf_layout_query(C.byref(cfg), C.byref(lay)), "lrfb_qmf_layout_query")
+    rec = np.empty(lay.record_bytes, np.uint8)
+    rec[lay.u_offset[0] : lay.u_offset[0] + u.size] = u.reshape(-1)
+    rec[lay.v_offset[0] : lay.v_offset[0] + v.size] = v.reshape(-1)
+    q = meta["quantization"]
+    qp = torch.tensor([[q["u"][0], q["u"][1], q["v"][0], q["v"][1], float(u.min()), float(v.min())]],
+                      dtype=torch.float32)
+    device = torch.device("cuda", torch.cuda.current_device())
+    with torch.cuda.device(device):
+        d_rec, d_qp = torch.from_numpy(rec).to(device), qp.to(device)
+        out = torch.empty((1, 3, H, W), dtype=torch.uint8, device=device)
+        rc = _cabi.lib().lrfb_svd_decode(C.byref(cfg), 1, C.c_void_p(d_rec.data_ptr()), C.c_void_p(d_qp.data_ptr()),
+                                         C.c_void_p(out.data_ptr()), _stream_ptr())
+        _cabi.check(rc, "lrfb_svd_decode")
+        return out[0].cpu()

@@ -41,13 +41,14 @@ __device__ inline int sturm_count(const double* d, const double* e, int N, doubl
   int cnt = p < 0.0;
 #pragma unroll 2
   for (int i = 1; i < N; ++i) {
-    double pn = fma(d[i] - x, p, -(e[i - 1] * e[i - 1]) * pm);
-    if (fabs(pn) < pivmin * fabs(p)) pn = -pivmin * p;
+    const double ei = e[i - 1];
+    double pn = fma(d[i] - x, p, -(ei * ei) * pm);
+    pn = fabs(pn) < pivmin * fabs(p) ? -pivmin * p : pn;
     cnt += (pn < 0.0) != (p < 0.0);
-    pm = p, p = pn;
-    double a = fabs(p);
-    if (a > 1e100) pm *= 1e-100, p *= 1e-100;
-    else if (a < 1e-100) pm *= 1e100, p *= 1e100;
+    // branch-free rescaling (probes of one warp would otherwise diverge here)
+    const double a = fabs(pn);
+    const double sc = a > 1e100 ? 1e-100 : (a < 1e-100 ? 1e100 : 1.0);
+    pm = p * sc, p = pn * sc;
   }
   return cnt;
 }

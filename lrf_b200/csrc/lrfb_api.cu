@@ -17,6 +17,7 @@
 #include "frontend.cuh"
 #include "gram.cuh"
 #include "lrfb_common.cuh"
+#include "svdcodec.cuh"
 
 using namespace lrfb;
 
@@ -409,10 +410,11 @@ SideStream* side_stream() {
 #endif
 
 int64_t encode_scratch_bytes(const Geometry& g, int batch) {
-  int64_t mx = 0;
+  int64_t mx = align_up((int64_t)batch * 16, 256);  // svd codec: per-image (min, max) of u and v
+  int64_t fw = 0;
   for (int pl = 0; pl < g.lay.n_planes; ++pl)
-    mx = std::max(mx, FactorWs::bytes(batch, g.lay.rows[pl], g.lay.cols, g.lay.rank[pl]));
-  return mx;
+    fw = std::max(fw, FactorWs::bytes(batch, g.lay.rows[pl], g.lay.cols, g.lay.rank[pl]));
+  return mx + fw;
 }
 
 // vectorised kernels apply: 8x8 patches, YCbCr, W % 16 == 0, chroma exactly half width, aligned base
@@ -640,6 +642,85 @@ LRFB_EXPORT int32_t lrfb_qmf_decode(const lrfb_qmf_config* cfg, int32_t batch, c
   }
   LRFB_LAUNCH(qmf_decode_kernel, grid, dim3(256), 0, (cudaStream_t)(uintptr_t)stream, d_factors, d_images, P);
   return check_launch("qmf_decode_kernel");
+}
+
+LRFB_EXPORT int32_t lrfb_svd_encode(const lrfb_qmf_config* cfg, int32_t batch, const void* d_images,
+                                    uint8_t* d_codes, float* d_qparams, void* d_workspace, int64_t workspace_bytes,
+                                    const lrfb_qmf_debug* dbg, void* stream) {
+  if (!d_images || !d_codes || !d_qparams || !d_workspace || batch <= 0) return fail(LRFB_E_ARG, "bad arguments");
+  if (!cfg || cfg->color_space != LRFB_RGB)
+    return fail(LRFB_E_UNSUPPORTED, "svd codec: only color_space RGB is implemented (the reference's YCbCr branch is broken)");
+  Geometry g;
+  int rc = make_geometry(cfg, batch, &g);
+  if (rc) return rc;
+  lrfb_qmf_workspace_map m;
+  make_map(g, batch, &m);
+  const int64_t need = m.total_bytes + encode_scratch_bytes(g, batch);
+  if (workspace_bytes < need) return fail(LRFB_E_WORKSPACE, "workspace %lld < required %lld bytes", (long long)workspace_bytes, (long long)need);
+  cudaStream_t st = (cudaStream_t)(uintptr_t)stream;
+  unsigned char* ws = reinterpret_cast<unsigned char*>(d_workspace);
+  float* xs[3] = {reinterpret_cast<float*>(ws + m.x[0]), nullptr, nullptr};
+  if ((rc = run_frontend(cfg, g, batch, d_images, xs, st))) return rc;
+  const lrfb_qmf_layout& L = g.lay;
+  const int M = L.rows[0], N = L.cols, R = L.rank[0];
+  float* u = reinterpret_cast<float*>(ws + m.u[0]);
+  float* v = reinterpret_cast<float*>(ws + m.v[0]);
+  double* evec = reinterpret_cast<double*>(ws + m.evec[0]);
+  double* sigma = reinterpret_cast<double*>(ws + m.sigma[0]);
+  float* mm = reinterpret_cast<float*>(ws + m.total_bytes);  // [2][batch][2]
+  unsigned char* scratch = ws + m.total_bytes + align_up((int64_t)batch * 16, 256);
+  rc = factorize_batch(xs[0], batch, M, N, R, -1.f, 1.f, 1, u, v, nullptr, nullptr, 0, nullptr, nullptr,
+                       dbg ? dbg->d_sign_flip[0] : nullptr, reinterpret_cast<double*>(ws + m.gram[0]), evec, sigma,
+                       scratch, 0, st, 1);
+  if (rc) return rc;
+  for (int m0 = 0; m0 < batch; m0 += 65535) {
+    const int cnt = std::min(65535, batch - m0);
+    const int gx = std::max(1, std::min((M + kProjRows - 1) / kProjRows, 256));
+    const size_t psmem = (size_t)N * R * 8 + (size_t)kProjRows * (N + 1) * 4;
+#ifndef LRFB_SIM
+    if (psmem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(svd_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
+      if (e != cudaSuccess) return fail((int)e, "project smem attribute: %s", cudaGetErrorString(e));
+    }
+#endif
+    LRFB_LAUNCH(svd_project_kernel, dim3(gx, cnt), dim3(kProjRows), psmem, st, xs[0] + (size_t)m0 * M * N,
+                (long long)M * N, M, N, R, evec + (size_t)m0 * N * R, sigma + (size_t)m0 * R, u + (size_t)m0 * M * R);
+    if ((rc = check_launch("svd_project_kernel"))) return rc;
+  }
+  LRFB_LAUNCH(minmax_kernel, dim3(batch), dim3(256), 0, st, u, (long long)M * R, mm);
+  if ((rc = check_launch("minmax_kernel"))) return rc;
+  LRFB_LAUNCH(minmax_kernel, dim3(batch), dim3(256), 0, st, v, (long long)N * R, mm + 2 * (size_t)batch);
+  if ((rc = check_launch("minmax_kernel"))) return rc;
+  for (int m0 = 0; m0 < batch; m0 += 65535) {
+    const int cnt = std::min(65535, batch - m0);
+    LRFB_LAUNCH(quantize_u8_kernel, dim3(std::min((M * R + 255) / 256, 256), cnt), dim3(256), 0, st,
+                u + (size_t)m0 * M * R, M, R, mm + 2 * (size_t)m0, d_codes + (size_t)m0 * L.record_bytes + L.u_offset[0],
+                (long long)L.record_bytes, d_qparams + 4 * (size_t)m0, 4LL);
+    if ((rc = check_launch("quantize_u8_kernel"))) return rc;
+    LRFB_LAUNCH(quantize_u8_kernel, dim3(std::min((N * R + 255) / 256, 256), cnt), dim3(256), 0, st,
+                v + (size_t)m0 * N * R, N, R, mm + 2 * (size_t)batch + 2 * (size_t)m0,
+                d_codes + (size_t)m0 * L.record_bytes + L.v_offset[0], (long long)L.record_bytes,
+                d_qparams + 4 * (size_t)m0 + 2, 4LL);
+    if ((rc = check_launch("quantize_u8_kernel"))) return rc;
+  }
+  return 0;
+}
+
+LRFB_EXPORT int32_t lrfb_svd_decode(const lrfb_qmf_config* cfg, int32_t batch, const uint8_t* d_codes,
+                                    const float* d_qparams6, uint8_t* d_images, void* stream) {
+  if (!d_codes || !d_qparams6 || !d_images || batch <= 0) return fail(LRFB_E_ARG, "bad arguments");
+  if (!cfg || cfg->color_space != LRFB_RGB) return fail(LRFB_E_UNSUPPORTED, "svd codec: only color_space RGB");
+  Geometry g;
+  int rc = make_geometry(cfg, batch, &g);
+  if (rc) return rc;
+  SvdDecodeParams P;
+  memset(&P, 0, sizeof(P));
+  P.H = cfg->height, P.W = cfg->width, P.p = cfg->patch_h, P.q = cfg->patch_w, P.n_img = batch, P.R = g.lay.rank[0];
+  P.g = g.fp.g[0], P.record_bytes = g.lay.record_bytes, P.u_off = g.lay.u_offset[0], P.v_off = g.lay.v_offset[0];
+  long long hw = (long long)cfg->height * cfg->width;
+  dim3 grid((unsigned)std::min<long long>((hw + 255) / 256, 8192), std::min(batch, 65535));
+  LRFB_LAUNCH(svd_decode_kernel, grid, dim3(256), 0, (cudaStream_t)(uintptr_t)stream, d_codes, d_qparams6, d_images, P);
+  return check_launch("svd_decode_kernel");
 }
 
 LRFB_EXPORT int32_t lrfb_sse_u8(const uint8_t* d_a, const uint8_t* d_b, int64_t elems_per_image, int32_t batch,

@@ -130,3 +130,32 @@ def sse(a, b):
     per = a.size // B
     _cabi.check(lib().lrfb_sse_u8(_ptr(a), _ptr(b), per, B, _ptr(out), None), "sse", lib())
     return out
+
+
+def svd_encode(images: np.ndarray, cfg, sign_flip=None):
+    images = np.ascontiguousarray(images)
+    B = images.shape[0]
+    L = layout(cfg)
+    m = _cabi.QmfWorkspaceMap()
+    _cabi.check(lib().lrfb_qmf_workspace_query(C.byref(cfg), B, C.byref(m)), "ws query", lib())
+    ws = np.zeros(m.total_bytes + 256, np.uint8)
+    codes = np.zeros((B, L.record_bytes), np.uint8)
+    qp = np.zeros((B, 4), np.float32)
+    dbg = _cabi.QmfDebug()
+    keep = None
+    if sign_flip is not None:
+        keep = np.ascontiguousarray(sign_flip, np.int32)
+        dbg.d_sign_flip[0] = keep.ctypes.data
+    rc = lib().lrfb_svd_encode(C.byref(cfg), B, _ptr(images), _ptr(codes), _ptr(qp), _ptr(ws), m.total_bytes,
+                               C.byref(dbg), None)
+    _cabi.check(rc, "svd_encode", lib())
+    return codes, qp, ws, m, L
+
+
+def svd_decode(codes: np.ndarray, qp6: np.ndarray, cfg):
+    B = codes.shape[0]
+    out = np.zeros((B, 3, cfg.height, cfg.width), np.uint8)
+    codes = np.ascontiguousarray(codes)
+    qp6 = np.ascontiguousarray(qp6, np.float32)
+    _cabi.check(lib().lrfb_svd_decode(C.byref(cfg), B, _ptr(codes), _ptr(qp6), _ptr(out), None), "svd_decode", lib())
+    return out

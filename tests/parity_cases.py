@@ -81,3 +81,12 @@ def check_decode(backend, manifest, name):
     assert hashlib.sha256(dec[0].tobytes()).hexdigest() == e["decoded_sha256"]
     sse = backend.sse(dec, img.numpy()[None])
     assert int(sse[0]) == exact.sse_u8(dec[0], img.numpy())
+
+
+def _svd_sign_flips(img, R, v0, patch=(8, 8)):
+    x = port.patchify(port.pad_image(img.float(), patch), patch)
+    _, S, Vh = torch.linalg.svd(x, full_matrices=False)
+    vref = (Vh[:R].T * torch.sqrt(S[:R])).numpy()
+    s = np.sign((v0 * vref).sum(0)).astype(np.int32)
+    s[s == 0] = 1
+    return s[None]
