@@ -69,7 +69,8 @@ def test_gpu_svd_encode_parity(manifest, name):
     assert torch.equal(lrf_b200.svd_decode(blob), dec_ref_decoder)
     psnr = port.psnr(img, dec_ref_decoder)
     assert abs(psnr - e["psnr"]) <= 0.01, (psnr, e["psnr"])
-    assert abs(len(blob) - e["bytes"]) <= 0.01 * e["bytes"], (len(blob), e["bytes"])
+    # column signs are not aligned with LAPACK's here: the affine uint8 codes (hence zlib) move by a few %
+    assert abs(len(blob) - e["bytes"]) <= 0.08 * e["bytes"], (len(blob), e["bytes"])
     # with LAPACK's signs the uint8 codes agree except at truncation boundaries
     meta, ur, vr = _ref_codes(golden_bytes(name))
     R = ur.shape[1]
@@ -86,3 +87,11 @@ def test_gpu_svd_encode_parity(manifest, name):
     vc = codes[0, lay.v_offset[0]:].reshape(R, -1).T.cpu().numpy()
     assert (uc != ur).mean() < 0.01, (uc != ur).mean()
     assert (vc != vr).mean() < 0.01, (vc != vr).mean()
+    # ... and so does the byte count (same packing as the reference's encode_tensor)
+    from lrf_b200 import packing
+
+    host = codes[0].cpu().numpy()
+    body = packing.combine_bytes([packing.encode_fibers(np.ascontiguousarray(uc.T), "uint8"),
+                                  packing.encode_fibers(np.ascontiguousarray(vc.T), "uint8")])
+    ref_body = port.separate_bytes(golden_bytes(name), 2)[1]
+    assert abs(len(body) - len(ref_body)) <= 0.01 * len(ref_body), (len(body), len(ref_body))
