@@ -297,7 +297,7 @@ def main():
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     fp32_peak = sms * 8 * 256 * it * 64 / (ff_ms / 1e3) / 1e12
     achieved_gbs = alg_bytes / (bcd_ms / 1e3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "bcd_kernel<64,4> (luma BCD sweeps)", "achieved": achieved_gbs,
+    roofline = {"bound": "hbm", "kernel": "bcd_resident_kernel<4,768,384>: all 10 BCD sweeps on the luma planes (lrfb_bcd)", "achieved": achieved_gbs,
                 "peak": peaks["hbm_gbs"], "peak_source": peak_src, "unit": "GB/s",
                 "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": None,
                 "ms_per_launch": bcd_ms, "algorithmic_bytes_per_launch": alg_bytes,

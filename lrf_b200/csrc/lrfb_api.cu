@@ -737,11 +737,15 @@ LRFB_EXPORT int32_t lrfb_sse_u8(const uint8_t* d_a, const uint8_t* d_b, int64_t 
 
 struct lrfb_ctx {
   int device;
-  cudaStream_t stream;
-  void* d_in;
+  cudaStream_t stream;   // compute + D2H
+  cudaStream_t copy;     // H2D
+  void* d_in;            // two chunk-sized input buffers back to back
   void* d_out;
   void* d_ws;
   size_t in_cap, out_cap, ws_cap;
+#ifndef LRFB_SIM
+  cudaEvent_t landed[2], consumed[2];
+#endif
 };
 
 #ifdef LRFB_SIM
@@ -801,9 +805,14 @@ LRFB_EXPORT int32_t lrfb_ctx_create(int32_t device, lrfb_ctx** out) {
   memset(c, 0, sizeof(*c));
   c->device = device;
   e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking);
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+    e = cudaEventCreateWithFlags(&c->landed[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->consumed[i], cudaEventDisableTiming);
+  }
   if (e != cudaSuccess) {
     delete c;
-    return fail((int)e, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    return fail((int)e, "lrfb_ctx_create: %s", cudaGetErrorString(e));
   }
   *out = c;
   return 0;
@@ -814,11 +823,16 @@ LRFB_EXPORT void lrfb_ctx_destroy(lrfb_ctx* c) {
   if (c->d_in) cudaFree(c->d_in);
   if (c->d_out) cudaFree(c->d_out);
   if (c->d_ws) cudaFree(c->d_ws);
+  for (int i = 0; i < 2; ++i) cudaEventDestroy(c->landed[i]), cudaEventDestroy(c->consumed[i]);
+  cudaStreamDestroy(c->copy);
   cudaStreamDestroy(c->stream);
   delete c;
 }
 #endif
 
+// Chunked, double-buffered pipeline: the H2D copy of chunk i+1 (copy stream) overlaps the kernels of chunk i
+// (compute stream); the int8 records of a chunk go back on the compute stream as soon as it finishes.  The
+// workspace is sized for one chunk, so host batches larger than device memory would allow still encode.
 LRFB_EXPORT int32_t lrfb_qmf_encode_host(lrfb_ctx* c, const lrfb_qmf_config* cfg, int32_t batch,
                                          const void* h_images, int8_t* h_factors) {
   if (!c || !h_images || !h_factors || batch <= 0) return fail(LRFB_E_ARG, "bad arguments");
@@ -826,20 +840,38 @@ LRFB_EXPORT int32_t lrfb_qmf_encode_host(lrfb_ctx* c, const lrfb_qmf_config* cfg
   lrfb_qmf_layout L;
   int rc;
   if ((rc = lrfb_qmf_layout_query(cfg, &L))) return rc;
-  if ((rc = lrfb_qmf_workspace_query(cfg, batch, &m))) return rc;
+  const size_t img_bytes = (size_t)3 * cfg->height * cfg->width * (cfg->input_dtype == LRFB_U8 ? 1 : 4);
+  // ~0.3 GB of input per chunk: long enough to hide launch latency, short enough to overlap well
+  int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)batch, ((size_t)320 << 20) / std::max<size_t>(img_bytes, 1)));
+  if ((rc = lrfb_qmf_workspace_query(cfg, chunk, &m))) return rc;
 #ifndef LRFB_SIM
   cudaSetDevice(c->device);
 #endif
-  size_t in_bytes = (size_t)batch * 3 * cfg->height * cfg->width * (cfg->input_dtype == LRFB_U8 ? 1 : 4);
-  size_t out_bytes = (size_t)batch * L.record_bytes;
-  if ((rc = grow(&c->d_in, &c->in_cap, in_bytes))) return rc;
-  if ((rc = grow(&c->d_out, &c->out_cap, out_bytes))) return rc;
+  if ((rc = grow(&c->d_in, &c->in_cap, 2 * (size_t)chunk * img_bytes))) return rc;
+  if ((rc = grow(&c->d_out, &c->out_cap, (size_t)chunk * L.record_bytes))) return rc;
   if ((rc = grow(&c->d_ws, &c->ws_cap, (size_t)m.total_bytes))) return rc;
-  if ((rc = h2d(c->d_in, h_images, in_bytes, c->stream))) return rc;
-  if ((rc = lrfb_qmf_encode(cfg, batch, c->d_in, (int8_t*)c->d_out, c->d_ws, m.total_bytes, nullptr,
-                            (void*)(uintptr_t)c->stream)))
-    return rc;
-  if ((rc = d2h(h_factors, c->d_out, out_bytes, c->stream))) return rc;
+  const unsigned char* src = reinterpret_cast<const unsigned char*>(h_images);
+  int idx = 0;
+  for (int i0 = 0; i0 < batch; i0 += chunk, ++idx) {
+    const int n = std::min(chunk, batch - i0);
+    const int slot = idx & 1;
+    unsigned char* d_in = reinterpret_cast<unsigned char*>(c->d_in) + (size_t)slot * chunk * img_bytes;
+#ifndef LRFB_SIM
+    if (idx >= 2) cudaStreamWaitEvent(c->copy, c->consumed[slot], 0);  // kernels of chunk idx-2 are done with it
+    if ((rc = h2d(d_in, src + (size_t)i0 * img_bytes, (size_t)n * img_bytes, c->copy))) return rc;
+    cudaEventRecord(c->landed[slot], c->copy);
+    cudaStreamWaitEvent(c->stream, c->landed[slot], 0);
+#else
+    if ((rc = h2d(d_in, src + (size_t)i0 * img_bytes, (size_t)n * img_bytes, c->stream))) return rc;
+#endif
+    if ((rc = lrfb_qmf_encode(cfg, n, d_in, (int8_t*)c->d_out, c->d_ws, m.total_bytes, nullptr,
+                              (void*)(uintptr_t)c->stream)))
+      return rc;
+#ifndef LRFB_SIM
+    cudaEventRecord(c->consumed[slot], c->stream);
+#endif
+    if ((rc = d2h(h_factors + (size_t)i0 * L.record_bytes, c->d_out, (size_t)n * L.record_bytes, c->stream))) return rc;
+  }
   return sync_stream(c->stream);
 }
 
