@@ -141,13 +141,15 @@ class EncodePlan:
         return self.workspace[off : off + n].view(dt).view(shape)
 
 
-def _check_encode_args(rank, quality, color_space, patch, dtype, kwargs):
+def _check_encode_args(rank, quality, color_space, patch, dtype, kwargs, bounds=None):
     assert (rank, quality) != (None, None), "Either 'rank' or 'quality' must be specified."
     assert color_space in ("RGB", "YCbCr"), "`color_space` must be one of 'RGB' or 'YCbCr'."
     if not patch:
         raise NotImplementedError("lrf_b200: patch=False is not on the accelerated path (SURVEY §8f.3)")
     if dtype != torch.int8:
         raise NotImplementedError("lrf_b200: only dtype=torch.int8 factors are implemented")
+    if bounds is not None and (math.ceil(bounds[0]) < -128 or math.floor(bounds[1]) > 127):
+        raise NotImplementedError("lrf_b200: bounds outside the int8 range are not implemented")
     extra = {k: v for k, v in kwargs.items() if k not in ("num_iters", "verbose")}
     for k, v in extra.items():
         if (k in ("l2", "l1_ratio") and v == 0) or (k == "num_levels" and v is None) or (k == "eps" and v == 1e-16):
@@ -166,7 +168,7 @@ def qmf_encode_batch(images: torch.Tensor, rank=None, quality=None, color_space:
                      dtype: torch.dtype = torch.int8, return_records: bool = False, **kwargs):
     """Batched ``qmf_encode``: images (B,3,H,W) → list of B encoded ``bytes`` (or, with
     ``return_records``, the raw int8 factor records on the device plus the layout / metadata)."""
-    _check_encode_args(rank, quality, color_space, patch, dtype, kwargs)
+    _check_encode_args(rank, quality, color_space, patch, dtype, kwargs, bounds)
     _require_cuda()
     assert images.ndim == 4 and images.shape[1] == 3, "images must be (B, 3, H, W)"
     device = images.device if images.is_cuda else torch.device("cuda", torch.cuda.current_device())

@@ -167,22 +167,23 @@ bcd_resident_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
           }
         }
       }
-      __syncthreads();
+      __syncwarp();  // the V-phase of a warp only touches the rows that same warp just updated
 
       // ---------------- V-phase: S[n][r] += X[m][n] * U[m][r] ----------------
-      // f32 within a <=64-row chunk (two half warps of <=32 rows each), chunk sums combined in f64.
+      // Half-warp h of warp w takes the 32*RT/2 rows w*32.. (+ h*NT ...) that warp w owns in the A-phase, so
+      // no CTA barrier separates the phases and warps drift apart (A-phase FMA/LDS overlaps V-phase of
+      // others).  f32 within the <=64-row chunk of a warp, chunk sums combined in f64 below.
       {
-        const int grp = tid >> 4, ln = tid & 15, w = tid >> 5;
-        constexpr int RPG = kResRows / NG;  // rows per half-warp group
-        static_assert(RPG <= 32, "one f32 chunk per group per sweep");
+        const int ln = tid & 15, w = tid >> 5, half = (tid >> 4) & 1;
+        static_assert(RT == 2, "row mapping below assumes two A-phase rows per thread");
         float sacc[4][R];
 #pragma unroll
         for (int c = 0; c < 4; ++c)
 #pragma unroll
           for (int r = 0; r < R; ++r) sacc[c][r] = 0.0f;
 #pragma unroll 4
-        for (int q = 0; q < RPG; ++q) {
-          const int row = grp + q * NG;
+        for (int q = 0; q < 32; ++q) {
+          const int row = w * 32 + q + half * NT;
           const float4 xv = *reinterpret_cast<const float4*>(&sm.x[row * N + ((ln ^ (row & 7)) << 2)]);
           float u[R];
           if (R == 4) {
