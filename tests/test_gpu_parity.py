@@ -225,3 +225,16 @@ def test_error_paths_on_device():
         lrf_b200.qmf_encode(port.s_nat(1, 32, 32), quality=7, bounds=(-200, 200))  # outside int8
     with pytest.raises(_cabi.LrfbError):
         lrf_b200.qmf_encode(port.s_nat(1, 3, 40), quality=7)  # reflect padding needs pad < dimension
+
+
+def test_eval_compression_mirror(manifest):
+    import lrf_b200
+
+    e = manifest["cases"]["snat9_128x192_q7"]
+    img = golden_image(e["image"])
+    out = lrf_b200.eval_compression(img, lrf_b200.qmf_encode, lrf_b200.qmf_decode, **README_KW)
+    assert set(out) == {"compression ratio", "bit rate (bpp)", "PSNR (dB)", "SSIM", "encoding time (ms)",
+                        "decoding time (ms)"}
+    assert abs(out["PSNR (dB)"] - e["psnr"]) < 0.05 and abs(out["bit rate (bpp)"] - e["bpp"]) < 0.02 * e["bpp"]
+    b = lrf_b200.eval_qmf_batch(torch.stack([img, img]), **README_KW)
+    assert abs(float(b["PSNR (dB)"][1]) - out["PSNR (dB)"]) < 1e-4
