@@ -545,13 +545,25 @@ LRFB_EXPORT int32_t lrfb_qmf_encode(const lrfb_qmf_config* cfg, int32_t batch, c
   SideStream* side = overlap ? side_stream() : nullptr;
   overlap = overlap && side;
   if (overlap) {
-    for (int pl = 0; pl < 3; ++pl)
-      if ((rc = run_plane(pl, 1, st))) return rc;
-    cudaEventRecord(side->fork, st);
-    cudaStreamWaitEvent(side->stream, side->fork, 0);
-    if ((rc = run_plane(0, 2, st))) return rc;
-    if ((rc = run_plane(1, 2, side->stream))) return rc;
-    if ((rc = run_plane(2, 2, side->stream))) return rc;
+    // With large batches (no Gram row split, hence no shared scratch) the whole chroma chain runs on the
+    // helper stream: the latency-bound eigen-solver of one plane overlaps the DMMA-bound Gram of another.
+    bool chains = !getenv("LRFB_NO_CHAIN_OVERLAP");
+    for (int pl = 0; pl < 3 && chains; ++pl) chains = FactorWs::gram_split(batch, L.rows[pl]) == 1;
+    if (chains) {
+      cudaEventRecord(side->fork, st);
+      cudaStreamWaitEvent(side->stream, side->fork, 0);
+      if ((rc = run_plane(0, 0, st))) return rc;
+      if ((rc = run_plane(1, 0, side->stream))) return rc;
+      if ((rc = run_plane(2, 0, side->stream))) return rc;
+    } else {
+      for (int pl = 0; pl < 3; ++pl)
+        if ((rc = run_plane(pl, 1, st))) return rc;
+      cudaEventRecord(side->fork, st);
+      cudaStreamWaitEvent(side->stream, side->fork, 0);
+      if ((rc = run_plane(0, 2, st))) return rc;
+      if ((rc = run_plane(1, 2, side->stream))) return rc;
+      if ((rc = run_plane(2, 2, side->stream))) return rc;
+    }
     cudaEventRecord(side->join, side->stream);
     cudaStreamWaitEvent(st, side->join, 0);
     return 0;
