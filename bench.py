@@ -267,25 +267,27 @@ def main():
     dbg = _cabi.QmfDebug()
     dbg.stop_after = 2
     plan.run(images, dbg)  # leaves the SVD init in u/v
-    u0, v0 = uy.clone(), vy.clone()
+    v0 = vy.clone()
+    so = plan.map.sigma[0] + B * lay.rank[0] * 8  # f32 singular values sit behind the f64 ones
+    s0y = plan.workspace[so: so + B * lay.rank[0] * 4].view(torch.float32).clone()
     wsb = 32768 * 16 * 4
     bws = torch.empty(wsb, dtype=torch.uint8, device=dev)
     My, N, Ry = lay.rows[0], lay.cols, lay.rank[0]
 
     def bcd_only():
         _cabi.check(lib.lrfb_bcd(C.c_void_p(xy.data_ptr()), B, My, N, Ry, -16.0, 15.0, KW["num_iters"],
-                                 C.c_void_p(uy.data_ptr()), C.c_void_p(vy.data_ptr()), C.c_void_p(bws.data_ptr()),
-                                 wsb, C.c_void_p(stream.cuda_stream)), "lrfb_bcd")
+                                 C.c_void_p(uy.data_ptr()), C.c_void_p(vy.data_ptr()), C.c_void_p(s0y.data_ptr()),
+                                 C.c_void_p(bws.data_ptr()), wsb, C.c_void_p(stream.cuda_stream)), "lrfb_bcd")
 
     bcd_ms = []
     for i in range(4):
-        uy.copy_(u0), vy.copy_(v0)
+        vy.copy_(v0)
         torch.cuda.synchronize()
         bcd_ms.append(cuda_time_ms(bcd_only))
     bcd_ms = statistics.median(bcd_ms[1:])
     plan.run(images)  # restore the full result
     # algorithmic work of that launch: X read once + U in/out + V in/out; flops per SURVEY §8(d) BCD row
-    alg_bytes = B * (My * N * 4 + 2 * My * Ry * 4 + 2 * N * Ry * 4)
+    alg_bytes = B * (My * N * 4 + My * Ry * 4 + 2 * N * Ry * 4)  # X once, U out, V in/out
     alg_flops = B * KW["num_iters"] * (4 * My * N * Ry + (My + N) * Ry * (4 * Ry + 4))
     peaks, peak_src = measured_peaks()
     # FP32 FFMA peak measured here (not in MEASURED_PEAKS.json)
@@ -296,10 +298,15 @@ def main():
                                                          C.c_void_p(stream.cuda_stream))) for _ in range(3))
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     fp32_peak = sms * 8 * 256 * it * 64 / (ff_ms / 1e3) / 1e12
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tp):  # dram__bytes_read+write of this kernel from the committed ncu --set full capture
+        with open(tp) as f:
+            traffic = json.load(f)["bytes_per_image"] * B
     achieved_gbs = alg_bytes / (bcd_ms / 1e3) / 1e9
     roofline = {"bound": "hbm", "kernel": "bcd_resident_kernel<4,768,384>: all 10 BCD sweeps on the luma planes (lrfb_bcd)", "achieved": achieved_gbs,
                 "peak": peaks["hbm_gbs"], "peak_source": peak_src, "unit": "GB/s",
-                "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": None,
+                "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": traffic,
                 "ms_per_launch": bcd_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "fp32": {"achieved_tflops": alg_flops / (bcd_ms / 1e3) / 1e12, "peak_tflops": fp32_peak,
                          "frac": alg_flops / (bcd_ms / 1e3) / 1e12 / fp32_peak,

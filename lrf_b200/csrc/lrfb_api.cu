@@ -606,8 +606,8 @@ LRFB_EXPORT int32_t lrfb_factorize(const float* d_x, int32_t n_mat, int32_t M, i
 LRFB_EXPORT int64_t lrfb_launch_count(void) { return g_launches; }
 
 LRFB_EXPORT int32_t lrfb_bcd(const float* d_x, int32_t n_mat, int32_t M, int32_t N, int32_t R, float bound_lo,
-                             float bound_hi, int32_t num_iters, float* d_u, float* d_v, void* d_workspace,
-                             int64_t workspace_bytes, void* stream) {
+                             float bound_hi, int32_t num_iters, float* d_u, float* d_v, const float* d_s0,
+                             void* d_workspace, int64_t workspace_bytes, void* stream) {
   if (!d_x || !d_u || !d_v || n_mat <= 0 || M <= 0 || N <= 0 || R <= 0 || num_iters <= 0)
     return fail(LRFB_E_ARG, "bad arguments");
   if (R > kGenMaxR || N > 1024) return fail(LRFB_E_UNSUPPORTED, "N=%d R=%d not implemented", N, R);
@@ -618,7 +618,7 @@ LRFB_EXPORT int32_t lrfb_bcd(const float* d_x, int32_t n_mat, int32_t M, int32_t
   BcdBatch b;
   b.X = d_x, b.x_stride = (long long)M * N, b.U = d_u, b.V = d_v, b.Uq = nullptr, b.Vq = nullptr;
   b.uq_stride = b.vq_stride = 0;
-  b.s0 = nullptr;
+  b.s0 = d_s0;
   b.M = M, b.n_mat = n_mat, b.num_iters = num_iters, b.lo = ceilf(bound_lo), b.hi = floorf(bound_hi);
   return run_bcd(b, N, R, reinterpret_cast<float*>(d_workspace), (cudaStream_t)(uintptr_t)stream);
 }
