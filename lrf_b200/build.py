@@ -13,7 +13,7 @@ OUT = os.path.join(CSRC, "build", "liblrfb.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     # every multiply/add that must stay separately rounded is written as such; FMAs are explicit
-    "-fmad=false", "-diag-suppress", "128",
+    "-fmad=false", "-diag-suppress", "128,177",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared",
 ]
 

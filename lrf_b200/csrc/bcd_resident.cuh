@@ -116,7 +116,7 @@ bcd_resident_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
         for (int i = 0; i < RT; ++i)
 #pragma unroll
           for (int r = 0; r < R; ++r) acc[i][r] = 0.0f;
-#pragma unroll 4
+#pragma unroll
         for (int k4 = 0; k4 < N / 4; ++k4) {
           float vk[4][R];
 #pragma unroll
@@ -175,15 +175,16 @@ bcd_resident_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
       // others).  f32 within the <=64-row chunk of a warp, chunk sums combined in f64 below.
       {
         const int ln = tid & 15, w = tid >> 5, half = (tid >> 4) & 1;
-        static_assert(RT == 2, "row mapping below assumes two A-phase rows per thread");
+        constexpr int HR = 16 * RT;  // rows per half warp: the warp's 32*RT A-phase rows split in two
         float sacc[4][R];
 #pragma unroll
         for (int c = 0; c < 4; ++c)
 #pragma unroll
           for (int r = 0; r < R; ++r) sacc[c][r] = 0.0f;
-#pragma unroll 4
-        for (int q = 0; q < 32; ++q) {
-          const int row = w * 32 + q + half * NT;
+#pragma unroll 16
+        for (int q = 0; q < HR; ++q) {
+          const int t = half * HR + q;  // index into the warp's row list
+          const int row = w * 32 + (t & 31) + (t >> 5) * NT;
           const float4 xv = *reinterpret_cast<const float4*>(&sm.x[row * N + ((ln ^ (row & 7)) << 2)]);
           float u[R];
           if (R == 4) {

@@ -262,6 +262,7 @@ int resident_variant() {
 template <int R>
 int launch_bcd_resident(const BcdBatch& b, cudaStream_t st) {
   if (resident_variant() == 0) return launch_bcd_resident_cfg<R, 768, 384, 8>(b, st);
+  if (resident_variant() == 2) return launch_bcd_resident_cfg<R, 768, 256, 8>(b, st);
   return launch_bcd_resident_cfg<R, 384, 192, 16>(b, st);
 }
 
@@ -273,9 +274,9 @@ bool resident_ok(int N, int R, int M) {
   }
   if (!enabled || N != 64 || R > 4 || bmm_native(N, M, R)) return false;
 #ifdef LRFB_SIM
-  return M <= (resident_variant() == 0 ? 768 : 384);  // the CPU shim has no clusters
+  return M <= (resident_variant() == 1 ? 384 : 768);  // the CPU shim has no clusters
 #else
-  return M <= (resident_variant() == 0 ? 8 * 768 : 16 * 384);
+  return M <= (resident_variant() == 1 ? 16 * 384 : 8 * 768);
 #endif
 }
 

@@ -172,6 +172,9 @@ inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
 inline float __fsqrt_rn(float a) { return std::sqrt(a); }
+inline float __fdividef(float a, float b) { volatile float r = a / b; return r * (1.0f + 1.1920929e-07f); }  // perturbed by 1 ulp on purpose
+
+
 inline float __frcp_rn(float a) { volatile float r = 1.0f / a; return r; }
 inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
 inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
