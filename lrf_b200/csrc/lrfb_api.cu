@@ -402,7 +402,10 @@ SideStream* side_stream() {
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
   SideStream& s = table[dev];
   if (!s.stream) {
-    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    // lowest priority: luma-chain blocks (caller's stream) are scheduled first, chroma fills what is left
+    int least = 0, greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&least, &greatest);
+    if (cudaStreamCreateWithPriority(&s.stream, cudaStreamNonBlocking, least) != cudaSuccess) return nullptr;
     cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming);
   }
