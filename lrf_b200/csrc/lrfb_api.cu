@@ -428,21 +428,28 @@ bool fast8_geometry(const Geometry& g, const void* base) {
          ((uintptr_t)base % 16) == 0;
 }
 
+// planes: bit 0 = plane 0 (luma / RGB), bit 1 = planes 1 and 2 (chroma)
 int run_frontend(const lrfb_qmf_config* cfg, const Geometry& g, int batch, const void* d_images,
-                 float* const* xs, cudaStream_t st) {
+                 float* const* xs, cudaStream_t st, int planes = 3) {
   if (cfg->input_dtype == LRFB_U8 && fast8_geometry(g, d_images)) {
     const unsigned char* img = (const unsigned char*)d_images;
-    long long items = (long long)g.fp.g[0].hp * g.fp.g[0].nbw;
-    dim3 grid((unsigned)std::min<long long>((items + 255) / 256, 4096), std::min(batch, 65535));
-    LRFB_LAUNCH(frontend8_luma_kernel, grid, dim3(256), 0, st, img, xs[0], g.fp);
-    int rc = check_launch("frontend8_luma_kernel");
-    if (rc) return rc;
-    items = (long long)g.fp.g[1].hp * g.fp.g[1].nbw;
-    dim3 grid2((unsigned)std::min<long long>((items + 255) / 256, 4096), std::min(batch, 65535));
-    LRFB_LAUNCH(frontend8_chroma_kernel, grid2, dim3(256), 0, st, img, xs[1], xs[2], g.fp);
-    return check_launch("frontend8_chroma_kernel");
+    if (planes & 1) {
+      long long items = (long long)g.fp.g[0].hp * g.fp.g[0].nbw;
+      dim3 grid((unsigned)std::min<long long>((items + 255) / 256, 4096), std::min(batch, 65535));
+      LRFB_LAUNCH(frontend8_luma_kernel, grid, dim3(256), 0, st, img, xs[0], g.fp);
+      int rc = check_launch("frontend8_luma_kernel");
+      if (rc) return rc;
+    }
+    if (planes & 2) {
+      long long items = (long long)g.fp.g[1].hp * g.fp.g[1].nbw;
+      dim3 grid2((unsigned)std::min<long long>((items + 255) / 256, 4096), std::min(batch, 65535));
+      LRFB_LAUNCH(frontend8_chroma_kernel, grid2, dim3(256), 0, st, img, xs[1], xs[2], g.fp);
+      return check_launch("frontend8_chroma_kernel");
+    }
+    return 0;
   }
   for (int pl = 0; pl < g.lay.n_planes; ++pl) {
+    if (!((pl == 0 ? 1 : 2) & planes)) continue;
     long long per_img = (long long)g.lay.rows[pl] * g.lay.cols;
     int gx = (int)std::min<long long>((per_img + 255) / 256, 8192);
     dim3 grid(gx, std::min(batch, 65535));
@@ -526,8 +533,6 @@ LRFB_EXPORT int32_t lrfb_qmf_encode(const lrfb_qmf_config* cfg, int32_t batch, c
   unsigned char* ws = reinterpret_cast<unsigned char*>(d_workspace);
   float* xs[3];
   for (int pl = 0; pl < 3; ++pl) xs[pl] = reinterpret_cast<float*>(ws + m.x[pl]);
-  if ((rc = run_frontend(cfg, g, batch, d_images, xs, st))) return rc;
-  if (dbg && dbg->stop_after == 1) return 0;
   const lrfb_qmf_layout& L = g.lay;
   auto run_plane = [&](int pl, int phase, cudaStream_t s) {
     return factorize_batch(xs[pl], batch, L.rows[pl], L.cols, L.rank[pl], cfg->bound_lo, cfg->bound_hi,
@@ -540,26 +545,29 @@ LRFB_EXPORT int32_t lrfb_qmf_encode(const lrfb_qmf_config* cfg, int32_t batch, c
                            dbg && dbg->stop_after == 2, s, phase);
   };
   // The planes are independent.  When every plane runs the shared-memory-resident sweeps (no shared scratch),
-  // all initialisations run first and the chroma sweeps go to a helper stream: the luma kernel occupies
-  // 15 clusters x 8 SMs, the chroma clusters fill the remaining SMs and take over as luma clusters retire.
+  // the chroma work goes to a low-priority helper stream: the luma sweeps occupy 15 clusters x 8 SMs, the
+  // chroma clusters fill the remaining SMs; with large batches (no Gram row split) the whole chroma chain
+  // (front end, Gram, eigen-solver, sweeps) runs there so the latency-bound eigen-solver of one plane
+  // overlaps the DMMA-bound Gram of another and the luma chain is the only critical path.
   bool overlap = false;
 #ifndef LRFB_SIM
-  overlap = L.n_planes == 3 && !(dbg && dbg->stop_after == 2) && cfg->num_iters > 0 && !getenv("LRFB_NO_OVERLAP");
+  overlap = L.n_planes == 3 && !(dbg && dbg->stop_after) && cfg->num_iters > 0 && !getenv("LRFB_NO_OVERLAP");
   for (int pl = 0; pl < L.n_planes && overlap; ++pl) overlap = resident_ok(L.cols, L.rank[pl], L.rows[pl]);
   SideStream* side = overlap ? side_stream() : nullptr;
   overlap = overlap && side;
   if (overlap) {
-    // With large batches (no Gram row split, hence no shared scratch) the whole chroma chain runs on the
-    // helper stream: the latency-bound eigen-solver of one plane overlaps the DMMA-bound Gram of another.
     bool chains = !getenv("LRFB_NO_CHAIN_OVERLAP");
     for (int pl = 0; pl < 3 && chains; ++pl) chains = FactorWs::gram_split(batch, L.rows[pl]) == 1;
     if (chains) {
-      cudaEventRecord(side->fork, st);
+      cudaEventRecord(side->fork, st);  // orders the helper stream after whatever produced d_images
       cudaStreamWaitEvent(side->stream, side->fork, 0);
+      if ((rc = run_frontend(cfg, g, batch, d_images, xs, st, 1))) return rc;
       if ((rc = run_plane(0, 0, st))) return rc;
+      if ((rc = run_frontend(cfg, g, batch, d_images, xs, side->stream, 2))) return rc;
       if ((rc = run_plane(1, 0, side->stream))) return rc;
       if ((rc = run_plane(2, 0, side->stream))) return rc;
     } else {
+      if ((rc = run_frontend(cfg, g, batch, d_images, xs, st))) return rc;
       for (int pl = 0; pl < 3; ++pl)
         if ((rc = run_plane(pl, 1, st))) return rc;
       cudaEventRecord(side->fork, st);
@@ -573,6 +581,8 @@ LRFB_EXPORT int32_t lrfb_qmf_encode(const lrfb_qmf_config* cfg, int32_t batch, c
     return 0;
   }
 #endif
+  if ((rc = run_frontend(cfg, g, batch, d_images, xs, st))) return rc;
+  if (dbg && dbg->stop_after == 1) return 0;
   for (int pl = 0; pl < L.n_planes; ++pl)
     if ((rc = run_plane(pl, 0, st))) return rc;
   return 0;

@@ -1,0 +1,86 @@
+"""Parity sweep on the GPU box: CUDA path vs the oracle port run live on the same machine.
+
+    python tools/parity_sweep.py [n_nat] [n_iid] > profiles/r1_parity_sweep.json
+
+For every image: (a) public API, signs not aligned: bytes, PSNR vs oracle; (b) SVD column signs aligned to
+LAPACK's (lrfb_qmf_debug.d_sign_flip): factors identical?, number of differing entries, decoded pixels max
+|diff|, PSNR delta.  Near-tie accounting comes from oracle/qmf_exact.c fed with the oracle's init.
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import lrf_b200
+from backends import GpuBackend, config_for, lapack_sign_flips, reference_planes, split_record
+from oracle import exact
+from oracle import qmf_port as port
+
+KW = dict(color_space="YCbCr", scale_factor=(0.5, 0.5), quality=7, patch=True, patch_size=(8, 8),
+          bounds=(-16, 15), dtype=torch.int8, num_iters=10)
+
+
+def main():
+    n_nat = int(sys.argv[1]) if len(sys.argv) > 1 else 48
+    n_iid = int(sys.argv[2]) if len(sys.argv) > 2 else 12
+    torch.set_num_threads(os.cpu_count() or 1)
+    gpu = GpuBackend()
+    rows = []
+    specs = [("s_nat", 5000 + i) for i in range(n_nat)] + [("s_iid", 7000 + i) for i in range(n_iid)]
+    t0 = time.time()
+    for kind, seed in specs:
+        img = port.s_nat(seed, 512, 768) if kind == "s_nat" else port.s_iid(seed, 512, 768)
+        blob_ref, ref, meta = port.qmf_encode(img, return_factors=True, **KW)
+        dec_ref = port.qmf_decode(blob_ref)
+        psnr_ref = port.psnr(img, dec_ref)
+        # (a) public API
+        blob = lrf_b200.qmf_encode(img, **KW)
+        dec = lrf_b200.qmf_decode(blob)
+        row = {"kind": kind, "seed": seed, "bytes_ref": len(blob_ref), "bytes_gpu_unaligned": len(blob),
+               "psnr_ref": psnr_ref, "psnr_gpu_unaligned": port.psnr(img, dec),
+               "decoders_agree": bool(torch.equal(dec, port.qmf_decode(blob)))}
+        # (b) signs aligned
+        cfg = config_for(img, KW, meta["rank"])
+        planes = reference_planes(img, KW)
+        inits = [port.svd_init(x.unsqueeze(0), meta["rank"][i]) for i, x in enumerate(planes)]
+        flips = lapack_sign_flips(gpu, img, cfg, [v.squeeze(0).numpy() for _, v in inits])
+        fac, _, L = gpu.encode(img.numpy()[None], cfg, sign_flip=flips)
+        got = split_record(fac[0], L)
+        diffs = [int((g != r.numpy()).sum()) for g, r in zip(got, ref)]
+        dec_al = gpu.decode(fac, cfg)[0]
+        meta_gpu = lrf_b200.compression._metadata(torch.uint8, "YCbCr", True, KW["bounds"], KW["patch_size"], L)
+        blob_al = lrf_b200.packing.pack_qmf_record(fac[0], L, meta_gpu)
+        near = 0
+        for i, x in enumerate(planes):  # near-tie count of the oracle's own trajectory (1e-5 window)
+            _, _, st = exact.bcd(x.numpy(), inits[i][0].squeeze(0).numpy(), inits[i][1].squeeze(0).numpy(),
+                                 KW["bounds"], KW["num_iters"])
+            near += st.near_ties
+        row.update({"factor_diffs_aligned": diffs, "identical_aligned": sum(diffs) == 0,
+                    "bytes_gpu_aligned": len(blob_al), "bytes_identical_aligned": blob_al == blob_ref,
+                    "psnr_gpu_aligned": port.psnr(img, torch.from_numpy(dec_al)),
+                    "max_pixel_diff_aligned": int(np.abs(dec_al.astype(int) - dec_ref.numpy().astype(int)).max()),
+                    "oracle_near_ties_1e-5": int(near)})
+        rows.append(row)
+    ident = sum(r["identical_aligned"] for r in rows)
+    out = {
+        "images": len(rows), "shape": [512, 768], "kwargs": "README (quality 7, 8x8, (-16,15), 10 iters)",
+        "host_threads": torch.get_num_threads(), "seconds": time.time() - t0,
+        "aligned_identical_factors": ident, "aligned_identical_bytes": sum(r["bytes_identical_aligned"] for r in rows),
+        "aligned_max_abs_dpsnr": max(abs(r["psnr_gpu_aligned"] - r["psnr_ref"]) for r in rows),
+        "aligned_max_pixel_diff": max(r["max_pixel_diff_aligned"] for r in rows),
+        "unaligned_max_abs_dpsnr": max(abs(r["psnr_gpu_unaligned"] - r["psnr_ref"]) for r in rows),
+        "unaligned_max_rel_dbytes": max(abs(r["bytes_gpu_unaligned"] - r["bytes_ref"]) / r["bytes_ref"] for r in rows),
+        "decoders_agree_all": all(r["decoders_agree"] for r in rows),
+        "rows": rows,
+    }
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()
