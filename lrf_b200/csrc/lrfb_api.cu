@@ -16,6 +16,7 @@
 #include "eig.cuh"
 #include "frontend.cuh"
 #include "gram.cuh"
+#include "gram_i8.cuh"
 #include "lrfb_common.cuh"
 #include "svdcodec.cuh"
 
@@ -307,7 +308,8 @@ int run_bcd(const BcdBatch& b, int N, int R, float* bwork, cudaStream_t st) {
 int factorize_batch(const float* x, int n_mat, int M, int N, int R, float lo, float hi, int iters, float* u,
                     float* v, int8_t* uq, int8_t* vq, long long q_stride, const float* init_u,
                     const float* init_v, const int32_t* sign_flip, double* gram, double* evec, double* sigma,
-                    unsigned char* scratch, int stop_after_init, cudaStream_t st, int phase = 0) {
+                    unsigned char* scratch, int stop_after_init, cudaStream_t st, int phase = 0,
+                    bool x_in_u8_range = false) {
   // phase 0: init + sweeps, 1: init only, 2: sweeps only (after a phase-1 call with the same arguments)
   int rc;
   const bool injected = init_u && init_v;
@@ -336,6 +338,20 @@ int factorize_batch(const float* x, int n_mat, int M, int N, int R, float lo, fl
       int cnt = std::min(65535, n_mat - m0);
       const float* xx = x + (size_t)m0 * M * N;
       double* go = gout + (size_t)m0 * split * N * N;
+#ifndef LRFB_SIM
+      static int use_i8 = -1;  // dev knob: LRFB_GRAM_I8=0 keeps the FP64 (DMMA) Gram for uint8-range planes too
+      if (use_i8 < 0) {
+        const char* ev = getenv("LRFB_GRAM_I8");
+        use_i8 = ev ? atoi(ev) : 1;
+      }
+      if (N == 64 && x_in_u8_range && use_i8 && (M + split - 1) / split <= 60000) {
+        // exact int8 tensor-core Gram (tcgen05): entries of X are in [0, 256)
+        const size_t ismem = sizeof(GramI8Smem) + 1024;
+        cudaError_t e = cudaFuncSetAttribute(gram64_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ismem);
+        if (e != cudaSuccess) return fail((int)e, "gram_i8 smem attribute: %s", cudaGetErrorString(e));
+        gram64_i8_kernel<<<dim3(split, cnt), dim3(kI8Threads), ismem, st>>>(xx, (long long)M * N, M, go, split);
+      } else
+#endif
       if (N == 64) {
         LRFB_LAUNCH(gram64_dmma_kernel, dim3(split, cnt), dim3(128), 0, st, xx, (long long)M * N, M, go, split);
       } else if (nblocks <= 160) {
@@ -542,7 +558,7 @@ LRFB_EXPORT int32_t lrfb_qmf_encode(const lrfb_qmf_config* cfg, int32_t batch, c
                            dbg ? dbg->d_init_v[pl] : nullptr, dbg ? dbg->d_sign_flip[pl] : nullptr,
                            reinterpret_cast<double*>(ws + m.gram[pl]), reinterpret_cast<double*>(ws + m.evec[pl]),
                            reinterpret_cast<double*>(ws + m.sigma[pl]), ws + m.total_bytes,
-                           dbg && dbg->stop_after == 2, s, phase);
+                           dbg && dbg->stop_after == 2, s, phase, cfg->input_dtype == LRFB_U8);
   };
   // The planes are independent.  When every plane runs the shared-memory-resident sweeps (no shared scratch),
   // the chroma work goes to a low-priority helper stream: the luma sweeps occupy 15 clusters x 8 SMs, the
