@@ -56,6 +56,7 @@ bcd_resident_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
   constexpr int RT = kResRows / NT;  // rows per thread in the A-phase
   constexpr int NG = NT / 16;        // half-warp row groups in the V-phase
   constexpr int NW = NT / 32;
+  constexpr int kRegRows = (R == 4 && ROWS == 768 && NT == 384) ? 1 : 0;  // register-resident A-phase row
   static_assert(kResRows % NT == 0, "thread shape");
   using S = ResSmem<R, ROWS, NT>;
   LRFB_DYN_SMEM(smem_raw);
@@ -103,6 +104,17 @@ bcd_resident_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
     cp_async_wait<0>();
     __syncthreads();
     gram_small<N, R>(sm.v, sm.b, tid);
+    // the first of this thread's A-phase rows stays in registers for all sweeps (no shared-memory reads
+    // for it in the A-phase; the V-phase still reads it from shared memory)
+    float xr[kRegRows ? N : 1];
+    if (kRegRows) {
+#pragma unroll
+      for (int k4 = 0; k4 < N / 4; ++k4) {
+        const float4 t4 = *reinterpret_cast<const float4*>(&sm.x[tid * N + ((k4 ^ (tid & 7)) << 2)]);
+        xr[(4 * k4 + 0) % (kRegRows ? N : 1)] = t4.x, xr[(4 * k4 + 1) % (kRegRows ? N : 1)] = t4.y;
+        xr[(4 * k4 + 2) % (kRegRows ? N : 1)] = t4.z, xr[(4 * k4 + 3) % (kRegRows ? N : 1)] = t4.w;
+      }
+    }
     __syncthreads();
 
     for (int it = 0; it < P.num_iters; ++it) {
@@ -126,7 +138,13 @@ bcd_resident_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
 #pragma unroll
           for (int i = 0; i < RT; ++i) {
             const int row = tid + i * NT;
-            const float4 xv = *reinterpret_cast<const float4*>(&sm.x[row * N + ((k4 ^ (row & 7)) << 2)]);
+            float4 xv;
+            if (kRegRows && i == 0) {
+              xv = make_float4(xr[(4 * k4 + 0) % (kRegRows ? N : 1)], xr[(4 * k4 + 1) % (kRegRows ? N : 1)],
+                               xr[(4 * k4 + 2) % (kRegRows ? N : 1)], xr[(4 * k4 + 3) % (kRegRows ? N : 1)]);
+            } else {
+              xv = *reinterpret_cast<const float4*>(&sm.x[row * N + ((k4 ^ (row & 7)) << 2)]);
+            }
 #pragma unroll
             for (int r = 0; r < R; ++r) {
               float a = acc[i][r];
