@@ -276,7 +276,7 @@ def main():
 
     def bcd_only():
         _cabi.check(lib.lrfb_bcd(C.c_void_p(xy.data_ptr()), B, My, N, Ry, -16.0, 15.0, KW["num_iters"],
-                                 C.c_void_p(uy.data_ptr()), C.c_void_p(vy.data_ptr()), C.c_void_p(s0y.data_ptr()),
+                                 C.c_void_p(uy.data_ptr()), C.c_void_p(vy.data_ptr()), C.c_void_p(s0y.data_ptr()), 1,
                                  C.c_void_p(bws.data_ptr()), wsb, C.c_void_p(stream.cuda_stream)), "lrfb_bcd")
 
     bcd_ms = []

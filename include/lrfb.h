@@ -122,10 +122,12 @@ int32_t lrfb_factorize(const float* d_x, int32_t n_mat, int32_t M, int32_t N, in
  * CoordinateDescent.forward :149-164) in place on d_u [n_mat][M][R] / d_v [n_mat][N][R].  On entry d_v holds
  * the initialisation v0; d_u holds u0 when d_s0 is NULL, otherwise d_u is output only and the first half-sweep
  * derives u0 = (X v0) / s from d_s0 [n_mat][R] (f32 singular values) exactly as lrfb_qmf_encode does.
- * Workspace: at least 32768*R*R bytes. */
+ * flags bit 0 (LRFB_X_IN_U8_RANGE): every entry of d_x lies in [0, 256) — true for the planes of the uint8 front
+ * end; allows the exact fixed-point tensor-core path for the X^T U half-sweep.  Workspace: at least 32768*R*R bytes. */
+#define LRFB_X_IN_U8_RANGE 1u
 int32_t lrfb_bcd(const float* d_x, int32_t n_mat, int32_t M, int32_t N, int32_t R, float bound_lo,
-                 float bound_hi, int32_t num_iters, float* d_u, float* d_v, const float* d_s0, void* d_workspace,
-                 int64_t workspace_bytes, void* stream);
+                 float bound_hi, int32_t num_iters, float* d_u, float* d_v, const float* d_s0, uint32_t flags,
+                 void* d_workspace, int64_t workspace_bytes, void* stream);
 
 /* Measurement helpers: number of kernels this library has launched so far (process-wide), and an FP32
  * FFMA throughput probe (launches num_SMs*8 blocks of 256 threads doing iters*32 dependent-chain FMAs on

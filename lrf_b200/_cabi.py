@@ -70,7 +70,8 @@ PROTOTYPES = {
                                    C.c_float, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "lrfb_bcd": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float,
-                             C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+                             C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int64,
+                             C.c_void_p]),
     "lrfb_launch_count": (C.c_int64, []),
     "lrfb_ffma_probe": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p]),
     "lrfb_svd_encode": (C.c_int32, [C.POINTER(QmfConfig), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -12,6 +12,7 @@
 
 #include "bcd.cuh"
 #include "bcd_resident.cuh"
+#include "bcd_tc.cuh"
 #include "decode.cuh"
 #include "eig.cuh"
 #include "frontend.cuh"
@@ -251,6 +252,45 @@ int launch_bcd_resident_cfg(const BcdBatch& b, cudaStream_t st) {
 #endif
 }
 
+#ifndef LRFB_SIM
+// resident sweeps with the V-phase on tcgen05 (int8, A operand in TMEM): N = 64, R <= 4, X in [0, 256)
+template <int R>
+int launch_bcd_tc(const BcdBatch& b, cudaStream_t st) {
+  const int need = (b.M + kTcRows - 1) / kTcRows;
+  int csize = 1;
+  while (csize < need) csize *= 2;
+  const int rows_per_cta = (b.M + csize - 1) / csize;
+  auto kern = bcd_tc_kernel<R>;
+  const size_t smem = sizeof(TcSmem<R>);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail((int)e, "bcd_tc smem attribute: %s", cudaGetErrorString(e));
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = csize, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(kTcThreads), cfg.dynamicSmemBytes = smem, cfg.stream = st, cfg.attrs = attr, cfg.numAttrs = 1;
+  cfg.gridDim = dim3(csize);
+  int max_clusters = 0;
+  e = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
+  if (e != cudaSuccess || max_clusters < 1) {
+    cudaGetLastError();
+    max_clusters = std::max(1, num_sms() / csize);
+  }
+  cfg.gridDim = dim3((unsigned)(std::min(b.n_mat, max_clusters) * csize));
+  e = cudaLaunchKernelEx(&cfg, kern, b, csize, rows_per_cta);
+  if (e != cudaSuccess) return fail((int)e, "bcd_tc launch: %s", cudaGetErrorString(e));
+  return check_launch("bcd_tc_kernel");
+}
+bool tc_enabled() {
+  static int v = -1;  // dev knob: LRFB_BCD_TC=0 keeps the FFMA V-phase
+  if (v < 0) {
+    const char* e = getenv("LRFB_BCD_TC");
+    v = e ? atoi(e) : 1;
+  }
+  return v != 0;
+}
+#endif
+
 int resident_variant() {
   static int v = -1;  // dev knob: LRFB_RES_VARIANT=0 (768 rows, 1 CTA/SM) | 1 (384 rows, 2 CTAs/SM)
   if (v < 0) {
@@ -282,6 +322,16 @@ bool resident_ok(int N, int R, int M) {
 }
 
 int run_bcd(const BcdBatch& b, int N, int R, float* bwork, cudaStream_t st) {
+#ifndef LRFB_SIM
+  if (resident_ok(N, R, b.M) && b.x_u8_range && tc_enabled() && b.M <= 8 * kTcRows) {
+    switch (R) {
+      case 1: return launch_bcd_tc<1>(b, st);
+      case 2: return launch_bcd_tc<2>(b, st);
+      case 3: return launch_bcd_tc<3>(b, st);
+      default: return launch_bcd_tc<4>(b, st);
+    }
+  }
+#endif
   if (resident_ok(N, R, b.M)) {
     switch (R) {
       case 1: return launch_bcd_resident<1>(b, st);
@@ -402,6 +452,7 @@ int factorize_batch(const float* x, int n_mat, int M, int N, int R, float lo, fl
   b.uq_stride = b.vq_stride = q_stride;
   b.M = M, b.n_mat = n_mat, b.num_iters = iters, b.lo = ceilf(lo), b.hi = floorf(hi);
   b.s0 = s0;
+  b.x_u8_range = x_in_u8_range ? 1 : 0;
   if (iters <= 0) return fail(LRFB_E_UNSUPPORTED, "num_iters must be >= 1");
   return run_bcd(b, N, R, bwork, st);
 }
@@ -637,7 +688,7 @@ LRFB_EXPORT int64_t lrfb_launch_count(void) { return g_launches; }
 
 LRFB_EXPORT int32_t lrfb_bcd(const float* d_x, int32_t n_mat, int32_t M, int32_t N, int32_t R, float bound_lo,
                              float bound_hi, int32_t num_iters, float* d_u, float* d_v, const float* d_s0,
-                             void* d_workspace, int64_t workspace_bytes, void* stream) {
+                             uint32_t flags, void* d_workspace, int64_t workspace_bytes, void* stream) {
   if (!d_x || !d_u || !d_v || n_mat <= 0 || M <= 0 || N <= 0 || R <= 0 || num_iters <= 0)
     return fail(LRFB_E_ARG, "bad arguments");
   if (R > kGenMaxR || N > 1024) return fail(LRFB_E_UNSUPPORTED, "N=%d R=%d not implemented", N, R);
@@ -649,6 +700,7 @@ LRFB_EXPORT int32_t lrfb_bcd(const float* d_x, int32_t n_mat, int32_t M, int32_t
   b.X = d_x, b.x_stride = (long long)M * N, b.U = d_u, b.V = d_v, b.Uq = nullptr, b.Vq = nullptr;
   b.uq_stride = b.vq_stride = 0;
   b.s0 = d_s0;
+  b.x_u8_range = (flags & 1u) ? 1 : 0;
   b.M = M, b.n_mat = n_mat, b.num_iters = num_iters, b.lo = ceilf(bound_lo), b.hi = floorf(bound_hi);
   return run_bcd(b, N, R, reinterpret_cast<float*>(d_workspace), (cudaStream_t)(uintptr_t)stream);
 }

@@ -36,7 +36,7 @@ for it in range(6):
     e0.record()
     _cabi.check(lib.lrfb_bcd(C.c_void_p(x.data_ptr()), B, lay.rows[0], lay.cols, lay.rank[0], -16.0, 15.0, 10,
                              C.c_void_p(u.data_ptr()), C.c_void_p(v.data_ptr()),
-                             C.c_void_p(s0.data_ptr()) if mode_s0 else None, C.c_void_p(ws.data_ptr()),
+                             C.c_void_p(s0.data_ptr()) if mode_s0 else None, 1, C.c_void_p(ws.data_ptr()),
                              ws.numel(), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "lrfb_bcd")
     e1.record()
     torch.cuda.synchronize()
