@@ -21,21 +21,19 @@
 
 namespace lrfb {
 
-constexpr int kTcRows = 768, kTcThreads = 384;
-constexpr int kTcColsA = kTcRows / 4;             // TMEM columns per A block (4 rows per cell)
-constexpr int kTcD1 = 400, kTcD2 = 416;           // accumulator columns
+constexpr int kTcRows = 768;  // largest row slice per CTA (1 CTA per SM); the 384-row shape runs 2 CTAs per SM
 
-template <int R>
+template <int R, int ROWS, int NT>
 struct TcSmem {
   static constexpr int N = 64;
-  float x[kTcRows * N];                 // swizzled f32 rows (A-phase)
-  unsigned char ub[kTcRows * 8];        // B operand: U as int8, K-major cores: (m/16)*128 + r*16 + m%16
+  float x[ROWS * N];                    // swizzled f32 rows (A-phase)
+  unsigned char ub[ROWS * 8];           // B operand: U as int8, K-major cores: (m/16)*128 + r*16 + m%16
   float v[N * R];
   float b[R * R];
   float b2[R * R];
   float a2[N * R];
   float s0inv[4];
-  int gred[(kTcThreads / 32) * R * R];
+  int gred[(NT / 32) * R * R];
   double comb[128 * 4];                 // per accumulator lane: slices already combined
   double part[2][N * R + R * R];
   unsigned long long mma_done, clear_done;
@@ -64,11 +62,16 @@ __device__ __forceinline__ void umma_i8_ts(unsigned tmem_d, unsigned tmem_a, uns
       : "memory");
 }
 
-template <int R>
-__global__ void __launch_bounds__(kTcThreads, 1)
+template <int R, int ROWS, int NT>
+__global__ void __launch_bounds__(NT, (ROWS <= 384 ? 2 : 1))  // 2 CTAs/SM: the tail of one overlaps the other's compute
 bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
-  constexpr int N = 64, NT = kTcThreads, RT = kTcRows / NT, NW = NT / 32;
-  using S = TcSmem<R>;
+  constexpr int N = 64, RT = ROWS / NT, NW = NT / 32;
+  constexpr int kTcRows = ROWS;
+  constexpr int kTcColsA = ROWS / 4;                        // TMEM columns per A block (4 rows per cell)
+  constexpr int kTcD1 = 2 * kTcColsA + 16, kTcD2 = kTcD1 + 16;  // accumulator columns
+  constexpr int kTmemCols = ROWS > 384 ? 512 : 256;
+  static_assert(ROWS % NT == 0 && ROWS % 64 == 0 && NW >= 4 && kTcD2 + 8 <= kTmemCols, "shape");
+  using S = TcSmem<R, ROWS, NT>;
   LRFB_DYN_SMEM(smem_raw);
   S& sm = *reinterpret_cast<S*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -91,7 +94,7 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(512));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(kTmemCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   for (int i = tid; i < kTcRows * 8; i += NT) sm.ub[i] = 0;
@@ -151,7 +154,8 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
       const int a_lo = l >> 6, n = l & 63;      // slice a_lo in block 0, a_lo + 2 in block 1
       const int sh0 = 24 - 8 * a_lo, sh1 = 8 - 8 * a_lo;
       const unsigned lane_addr = tmem + ((unsigned)((warp & 3) * 32) << 16);
-      for (int ch = warp >> 2; ch < kTcRows / 64; ch += NW / 4) {  // 64 rows (16 cells) per store
+      const int sharers = (NW - (warp & 3) + 3) / 4;  // warps that own this TMEM lane quarter
+      for (int ch = warp >> 2; ch < kTcRows / 64; ch += sharers) {  // 64 rows (16 cells) per store
         unsigned w0[16], w1[16];
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
@@ -171,13 +175,18 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
-    float xr[(R == 4) ? N : 1];  // first A-phase row of this thread stays in registers
-    if (R == 4) {
+    // the first kReg A-phase rows of this thread stay in registers for all sweeps
+    constexpr int kReg = (NT == 128) ? 2 : (R == 4 ? 1 : 0);
+    constexpr int kRegN = kReg ? N : 1;
+    float xr[kReg ? kReg : 1][kRegN];
+#pragma unroll
+    for (int i = 0; i < kReg; ++i) {
+      const int row = tid + i * NT;
 #pragma unroll
       for (int k4 = 0; k4 < N / 4; ++k4) {
-        const float4 t4 = *reinterpret_cast<const float4*>(&sm.x[tid * N + ((k4 ^ (tid & 7)) << 2)]);
-        xr[(4 * k4 + 0) % (R == 4 ? N : 1)] = t4.x, xr[(4 * k4 + 1) % (R == 4 ? N : 1)] = t4.y;
-        xr[(4 * k4 + 2) % (R == 4 ? N : 1)] = t4.z, xr[(4 * k4 + 3) % (R == 4 ? N : 1)] = t4.w;
+        const float4 t4 = *reinterpret_cast<const float4*>(&sm.x[row * N + ((k4 ^ (row & 7)) << 2)]);
+        xr[i][(4 * k4 + 0) % kRegN] = t4.x, xr[i][(4 * k4 + 1) % kRegN] = t4.y;
+        xr[i][(4 * k4 + 2) % kRegN] = t4.z, xr[i][(4 * k4 + 3) % kRegN] = t4.w;
       }
     }
     float uown[RT][R];  // this thread's U rows live in registers across the sweeps
@@ -206,9 +215,11 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
           for (int i = 0; i < RT; ++i) {
             const int row = tid + i * NT;
             float4 xv;
-            if (R == 4 && i == 0) {
-              xv = make_float4(xr[(4 * k4 + 0) % (R == 4 ? N : 1)], xr[(4 * k4 + 1) % (R == 4 ? N : 1)],
-                               xr[(4 * k4 + 2) % (R == 4 ? N : 1)], xr[(4 * k4 + 3) % (R == 4 ? N : 1)]);
+            if (i < kReg) {
+              constexpr int z = 0;
+              const int ii = i < kReg ? i : z;
+              xv = make_float4(xr[ii][(4 * k4 + 0) % kRegN], xr[ii][(4 * k4 + 1) % kRegN],
+                               xr[ii][(4 * k4 + 2) % kRegN], xr[ii][(4 * k4 + 3) % kRegN]);
             } else {
               xv = *reinterpret_cast<const float4*>(&sm.x[row * N + ((k4 ^ (row & 7)) << 2)]);
             }
@@ -380,7 +391,7 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
   if (cluster_size > 1) cluster.sync();  // nobody leaves while its partials may still be read
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
 }
 
 }  // namespace lrfb

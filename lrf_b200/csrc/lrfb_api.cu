@@ -226,6 +226,7 @@ int launch_bcd_resident_cfg(const BcdBatch& b, cudaStream_t st) {
 #else
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail((int)e, "bcd_resident smem attribute: %s", cudaGetErrorString(e));
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (csize > 8) {
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e != cudaSuccess) return fail((int)e, "non-portable cluster size: %s", cudaGetErrorString(e));
@@ -254,32 +255,62 @@ int launch_bcd_resident_cfg(const BcdBatch& b, cudaStream_t st) {
 
 #ifndef LRFB_SIM
 // resident sweeps with the V-phase on tcgen05 (int8, A operand in TMEM): N = 64, R <= 4, X in [0, 256)
-template <int R>
-int launch_bcd_tc(const BcdBatch& b, cudaStream_t st) {
-  const int need = (b.M + kTcRows - 1) / kTcRows;
+template <int R, int ROWS, int NT>
+int launch_bcd_tc_cfg(const BcdBatch& b, cudaStream_t st) {
+  const int need = (b.M + ROWS - 1) / ROWS;
   int csize = 1;
   while (csize < need) csize *= 2;
   const int rows_per_cta = (b.M + csize - 1) / csize;
-  auto kern = bcd_tc_kernel<R>;
-  const size_t smem = sizeof(TcSmem<R>);
+  auto kern = bcd_tc_kernel<R, ROWS, NT>;
+  const size_t smem = sizeof(TcSmem<R, ROWS, NT>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail((int)e, "bcd_tc smem attribute: %s", cudaGetErrorString(e));
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (csize > 8) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return fail((int)e, "non-portable cluster size: %s", cudaGetErrorString(e));
+  }
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = csize, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-  cfg.blockDim = dim3(kTcThreads), cfg.dynamicSmemBytes = smem, cfg.stream = st, cfg.attrs = attr, cfg.numAttrs = 1;
+  cfg.blockDim = dim3(NT), cfg.dynamicSmemBytes = smem, cfg.stream = st, cfg.attrs = attr, cfg.numAttrs = 1;
   cfg.gridDim = dim3(csize);
   int max_clusters = 0;
   e = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
   if (e != cudaSuccess || max_clusters < 1) {
     cudaGetLastError();
-    max_clusters = std::max(1, num_sms() / csize);
+    max_clusters = std::max(1, num_sms() * (ROWS <= 384 ? 2 : 1) / csize);
   }
+  if (const char* ov = getenv("LRFB_TC_CLUSTERS")) max_clusters = std::max(1, atoi(ov) * 8 / csize);  // dev knob (per 8-CTA unit)
   cfg.gridDim = dim3((unsigned)(std::min(b.n_mat, max_clusters) * csize));
+  if (getenv("LRFB_DEBUG")) {
+    int per_sm = -1;
+    cudaFuncAttributes fa;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem);
+    cudaFuncGetAttributes(&fa, kern);
+    fprintf(stderr, "[lrfb] bcd_tc blocks/SM=%d regs=%d static_smem=%zu max_dyn=%d\n", per_sm, fa.numRegs, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes);
+  }
+  if (getenv("LRFB_DEBUG"))
+    fprintf(stderr, "[lrfb] bcd_tc R=%d rows/cta=%d threads=%d cluster=%d max_active_clusters=%d grid=%u smem=%zu\n",
+            R, ROWS, NT, csize, max_clusters, cfg.gridDim.x, smem);
   e = cudaLaunchKernelEx(&cfg, kern, b, csize, rows_per_cta);
   if (e != cudaSuccess) return fail((int)e, "bcd_tc launch: %s", cudaGetErrorString(e));
   return check_launch("bcd_tc_kernel");
+}
+int tc_variant() {
+  static int v = -1;  // dev knob: LRFB_TC_VARIANT=0 (768 rows x 384 threads, 1 CTA/SM) | 1 (384 x 192, 2 CTAs/SM)
+  if (v < 0) {
+    const char* e = getenv("LRFB_TC_VARIANT");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+template <int R>
+int launch_bcd_tc(const BcdBatch& b, cudaStream_t st) {
+  if (tc_variant() == 1) return launch_bcd_tc_cfg<R, 384, 192>(b, st);
+  if (tc_variant() == 2) return launch_bcd_tc_cfg<R, 384, 128>(b, st);
+  return launch_bcd_tc_cfg<R, 768, 384>(b, st);
 }
 bool tc_enabled() {
   static int v = -1;  // dev knob: LRFB_BCD_TC=0 keeps the FFMA V-phase
