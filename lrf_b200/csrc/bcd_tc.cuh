@@ -21,22 +21,32 @@
 
 namespace lrfb {
 
-constexpr int kTcRows = 768;  // largest row slice per CTA (1 CTA per SM); the 384-row shape runs 2 CTAs per SM
-
+constexpr int kTcRows = 768;       // largest row slice per CTA
+constexpr int kTcMaxCluster = 8;   // portable cluster size
+// Per-sweep exchange — no cluster barrier and no all-to-all of the partial sums on the critical path (DSMEM moves
+// only ~20 B/cycle/SM, so a 2 KB x 8 all-to-all alone costs ~750 cycles):
+//   1. reduce-scatter: rank c OWNS the 64/C columns n in [c*64/C, (c+1)*64/C).  After the tensor core has finished a
+//      CTA's X^T U and U^T U partials, the four epilogue warps turn them into Q.24 fixed-point int64 (exact) and
+//      PUSH (st.async) each column's sums to its owner only; the 4 x 4 U^T U partial goes to every rank.  Pushes
+//      signal the receiver's `full` transaction mbarrier.
+//   2. the owner adds the <= 8 slots (integers: order-free), runs the Gauss–Seidel update of its 64/C rows of V and
+//      pushes each new row (16 B) to every rank (`vfull` mbarrier) — the all-gather.
+//   3. two warps per CTA copy the 64 gathered rows into V and form V^T V (exact integers, REDUX).
+// The receive buffers are single-buffered; a split cluster barrier (relaxed arrive after they were consumed, wait
+// just before the next push — long satisfied by then) protects them.
 template <int R, int ROWS, int NT>
 struct TcSmem {
   static constexpr int N = 64;
   float x[ROWS * N];                    // swizzled f32 rows (A-phase)
   unsigned char ub[ROWS * 8];           // B operand: U as int8, K-major cores: (m/16)*128 + r*16 + m%16
   float v[N * R];
-  float b[R * R];
-  float b2[R * R];
-  float a2[N * R];
+  float b[R * R];                       // V^T V of the float initialisation (first sweep of a matrix)
+  int bi[2][16];                        // V^T V halves of the two gather warps (integer V, later sweeps)
   float s0inv[4];
-  int gred[(NT / 32) * R * R];
-  double comb[128 * 4];                 // per accumulator lane: slices already combined
-  double part[2][N * R + R * R];
-  unsigned long long mma_done, clear_done;
+  alignas(16) longlong2 srecv[128];     // [source rank][owned column][r pair]: Q.24 sums of X^T U
+  alignas(16) int4 grecv[kTcMaxCluster * 4];  // [source rank][j]: row j of that rank's U^T U
+  alignas(16) float4 vrecv[N];          // gathered new rows of V (padded to 4 columns)
+  unsigned long long mma_done, clear_done, full, vfull;
   unsigned tmem_base;
 };
 
@@ -52,6 +62,31 @@ __device__ __forceinline__ void tmem_ld8(unsigned taddr, unsigned (&v)[8]) {
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld4(unsigned taddr, unsigned (&v)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+               : "r"(taddr));
+}
+__device__ __forceinline__ unsigned map_to_rank(unsigned cta_smem_addr, unsigned rank) {
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void push_2x64(unsigned remote, long long a, long long b, unsigned remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];" ::"r"(remote),
+               "l"(a), "l"(b), "r"(remote_bar)
+               : "memory");
+}
+__device__ __forceinline__ void push_4x32(unsigned remote, int a, int b, int c, int d, unsigned remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(remote),
+               "r"(a), "r"(b), "r"(c), "r"(d), "r"(remote_bar)
+               : "memory");
+}
+// relaxed: the slot reads this arrive publishes have already returned their values (they fed the V update that
+// every thread passed a CTA barrier after), so no fence (MEMBAR.ALL.GPU + ERRBAR per thread and sweep) is needed
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ void umma_i8_ts(unsigned tmem_d, unsigned tmem_a, unsigned long long b, unsigned idesc,
                                            unsigned accumulate) {
   asm volatile(
@@ -62,19 +97,31 @@ __device__ __forceinline__ void umma_i8_ts(unsigned tmem_d, unsigned tmem_a, uns
       : "memory");
 }
 
+#ifdef LRFB_TC_TRACE
+__device__ long long g_tc_trace[16 * 12];  // probe build only (tools/probes/tc_trace.cu): clock64 at 9 points of every sweep
+#define TC_TRACE(pt) \
+  if (blockIdx.x == 0 && tid == 0 && mat == cluster_id && it < 12) g_tc_trace[(pt) * 12 + it] = clock64();
+#define TC_TRACE_S(pt) \
+  if (blockIdx.x == 0 && tid == 0 && mat == cluster_id + n_clusters) g_tc_trace[14 * 12 + (pt)] = clock64();
+#else
+#define TC_TRACE(pt)
+#define TC_TRACE_S(pt)
+#endif
+
 template <int R, int ROWS, int NT>
 __global__ void __launch_bounds__(NT, (ROWS <= 384 ? 2 : 1))  // 2 CTAs/SM: the tail of one overlaps the other's compute
 bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
   constexpr int N = 64, RT = ROWS / NT, NW = NT / 32;
   constexpr int kTcRows = ROWS;
   constexpr int kTcColsA = ROWS / 4;                        // TMEM columns per A block (4 rows per cell)
-  constexpr int kTcD1 = 2 * kTcColsA + 16, kTcD2 = kTcD1 + 16;  // accumulator columns
+  constexpr int kTcD1 = 2 * kTcColsA + 16, kTcD2 = kTcD1 + 16, kTcD3 = kTcD2 + 16;  // accumulator columns
   constexpr int kTmemCols = ROWS > 384 ? 512 : 256;
-  static_assert(ROWS % NT == 0 && ROWS % 64 == 0 && NW >= 4 && kTcD2 + 8 <= kTmemCols, "shape");
+  static_assert(ROWS % NT == 0 && ROWS % 64 == 0 && NW >= 4 && kTcD3 + 8 <= kTmemCols, "shape");
   using S = TcSmem<R, ROWS, NT>;
   LRFB_DYN_SMEM(smem_raw);
   S& sm = *reinterpret_cast<S*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);  // same value, but provably warp-uniform (descriptor math in URs)
   const int M = P.M;
   cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
   const int crank = (int)cluster.block_rank();
@@ -85,12 +132,15 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
   const bool from_a = P.s0 != nullptr;
   const int row0 = crank * rows_per_cta;
   const int rows_here = max(0, min(rows_per_cta, M - row0));
-  int pbuf = 0;
-  unsigned mma_phase = 0;
+  unsigned mma_phase = 0, full_phase = 0;
+  const int npr = N / cluster_size, npr_log = 6 - (31 - __clz(cluster_size));  // columns of V owned per rank
+  int sweeps_done = 0;
 
   if (tid == 0) {
     mbar_init(&sm.mma_done, NW);  // one tcgen05.commit per warp and sweep
     mbar_init(&sm.clear_done, 1);
+    mbar_init(&sm.full, 1);       // one arrive.expect_tx per sweep + the bytes of all ranks' pushes
+    mbar_init(&sm.vfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -105,28 +155,33 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
   const unsigned tmem = sm.tmem_base;
   // D = s32, A = u8 (TMEM), B = s8 K-major, N = 8, M = 128
   const unsigned idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((8u >> 3) << 17) | ((128u >> 4) << 24);
+  const unsigned idesc_ss = idesc | (1u << 7);  // U^T U: A = the same int8 U tile read from shared memory (s8 x s8)
   // The accumulators are never cleared between sweeps: integer accumulation is exact and order-free, so every
   // warp issues the MMAs of its own rows as soon as they are projected, and the epilogue takes differences
   // (mod 2^32) against the previous sweep's totals.  One product against the all-zero B zeroes them here.
-  int prev1[8], prev2[8];
+  int prev1[4], prev2[4], prev3[4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) prev1[i] = prev2[i] = 0;
+  for (int i = 0; i < 4; ++i) prev1[i] = prev2[i] = prev3[i] = 0;
   if (tid == 0) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     const unsigned long long bd0 = umma_desc(smem_u32(sm.ub), 128, 128);
     umma_i8_ts(tmem + kTcD1, tmem, bd0, idesc, 0);
     umma_i8_ts(tmem + kTcD2, tmem + kTcColsA, bd0, idesc, 0);
+    umma_i8(tmem + kTcD3, umma_desc(smem_u32(sm.ub), 128, 0), bd0, idesc_ss, 0);
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&sm.clear_done)) : "memory");
   }
   mbar_wait(&sm.clear_done, 0);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  cluster.sync();  // every peer's mbarriers are initialised before anyone pushes
 
   for (int mat = cluster_id; mat < P.n_mat; mat += n_clusters) {
     const float* X = P.X + (size_t)mat * P.x_stride;
     float* V = P.V + (size_t)mat * N * R;
 
     // ---- load this CTA's slice of X once (swizzled f32) and V ----
+    TC_TRACE_S(0)
     __syncthreads();
+    TC_TRACE_S(1)
     for (int c = tid; c < kTcRows * (N / 4); c += NT) {
       const int row = c >> 4, ch = c & 15;
       float* dst = &sm.x[row * N + ((ch ^ (row & 7)) << 2)];
@@ -134,6 +189,15 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
       else dst[0] = dst[1] = dst[2] = dst[3] = 0.0f;
     }
     cp_async_commit();
+    // pull this CTA's slice of the NEXT matrix into L2 while HBM is otherwise idle during the sweeps
+#ifndef LRFB_TC_NO_PREFETCH
+    if (mat + n_clusters < P.n_mat && rows_here > 0) {
+      const char* nx = reinterpret_cast<const char*>(P.X + (size_t)(mat + n_clusters) * P.x_stride + (size_t)row0 * N);
+      const int bytes = rows_here * N * 4;
+      for (int o = tid * 4096; o < bytes; o += NT * 4096)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nx + o), "r"(min(4096, bytes - o)) : "memory");
+    }
+#endif
     for (int i = tid; i < N * R; i += NT) sm.v[i] = V[i];
     if (tid < R) {
       float inv = 0.0f;
@@ -144,37 +208,45 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
       sm.s0inv[tid] = inv;
     }
     const float* Uinit = P.U + (size_t)mat * M * R + (size_t)row0 * R;
+    TC_TRACE_S(2)
     cp_async_wait<0>();
     __syncthreads();
+    TC_TRACE_S(3)
     gram_small<N, R>(sm.v, sm.b, tid);
+    TC_TRACE_S(4)
 
     // ---- Q8.24 byte planes of X into tensor memory (A operand of the V-phase MMAs) ----
     {
       const int l = (warp & 3) * 32 + lane;     // accumulator / operand lane of this thread's TMEM quarter
-      const int a_lo = l >> 6, n = l & 63;      // slice a_lo in block 0, a_lo + 2 in block 1
-      const int sh0 = 24 - 8 * a_lo, sh1 = 8 - 8 * a_lo;
+      const int a_lo = l & 1, n = l >> 1;       // slice a_lo in block 0, a_lo + 2 in block 1 (lane pairs share n)
+      // floor(x * 2^24) = hi16 << 16 | lo16 without the quarter-rate F2I: hi16 = floor(256 x) and lo16 = floor(65536 frac)
+      // are read off the mantissas of round-toward-zero FMAs onto 2^23.  Slices 0/1 are the bytes 1/0 of hi16,
+      // slices 2/3 those of lo16: block 0 (slice a_lo) comes from hi16, block 1 (slice a_lo + 2) from lo16.
+      const unsigned sel = (1u - a_lo) | ((5u - a_lo) << 4);
       const unsigned lane_addr = tmem + ((unsigned)((warp & 3) * 32) << 16);
       const int sharers = (NW - (warp & 3) + 3) / 4;  // warps that own this TMEM lane quarter
       for (int ch = warp >> 2; ch < kTcRows / 64; ch += sharers) {  // 64 rows (16 cells) per store
         unsigned w0[16], w1[16];
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
-          unsigned p0 = 0, p1 = 0;
+          unsigned yh[4], yl[4];
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             const int m = ch * 64 + c * 4 + t;
             const float xv = sm.x[m * N + (((n >> 2) ^ (m & 7)) << 2) + (n & 3)];
-            const unsigned fx = __float2uint_rz(xv * 16777216.0f);
-            p0 |= ((fx >> sh0) & 0xffu) << (8 * t);
-            p1 |= ((fx >> sh1) & 0xffu) << (8 * t);
+            const float h = __fmaf_rz(xv, 256.0f, 8388608.0f);                       // 2^23 + floor(256 x)
+            const float frac = __fmaf_rn(xv, 256.0f, -__fadd_rn(h, -8388608.0f));     // exact, in [0, 1)
+            yh[t] = __float_as_uint(h), yl[t] = __float_as_uint(__fmaf_rz(frac, 65536.0f, 8388608.0f));
           }
-          w0[c] = p0, w1[c] = p1;
+          w0[c] = __byte_perm(__byte_perm(yh[0], yh[1], sel), __byte_perm(yh[2], yh[3], sel), 0x5410);
+          w1[c] = __byte_perm(__byte_perm(yl[0], yl[1], sel), __byte_perm(yl[2], yl[3], sel), 0x5410);
         }
         tmem_st16(lane_addr + ch * 16, w0);
         tmem_st16(lane_addr + kTcColsA + ch * 16, w1);
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
+    TC_TRACE_S(5)
     // the first kReg A-phase rows of this thread stay in registers for all sweeps
     constexpr int kReg = (NT == 128) ? 2 : (R == 4 ? 1 : 0);
     constexpr int kRegN = kReg ? N : 1;
@@ -192,12 +264,11 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
     float uown[RT][R];  // this thread's U rows live in registers across the sweeps
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    TC_TRACE_S(6)
 
     for (int it = 0; it < P.num_iters; ++it) {
       // ---------------- A-phase + Gauss–Seidel (identical arithmetic to bcd_resident_kernel) ----------------
-      int gacc[R * (R + 1) / 2];
-#pragma unroll
-      for (int i = 0; i < R * (R + 1) / 2; ++i) gacc[i] = 0;
+      TC_TRACE(0)
       {
         float acc[RT][R];
 #pragma unroll
@@ -234,6 +305,10 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
             }
           }
         }
+        TC_TRACE(1)
+        float breg[R * R];  // V^T V: float chain of the initialisation in the first sweep, exact integers afterwards
+#pragma unroll
+        for (int e = 0; e < R * R; ++e) breg[e] = it == 0 ? sm.b[e] : (float)(sm.bi[0][e] + sm.bi[1][e]);
 #pragma unroll
         for (int i = 0; i < RT; ++i) {
           const int row = tid + i * NT;
@@ -251,125 +326,155 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
 #pragma unroll
             for (int r = 0; r < R; ++r) f[r] = uown[i][r];
           }
-          gs_row<R>(f, acc[i], sm.b, t2_native_u, P.lo, P.hi);
+          gs_row<R>(f, acc[i], breg, t2_native_u, P.lo, P.hi);
 #pragma unroll
           for (int r = 0; r < R; ++r) {
             if (!ok) f[r] = 0.0f;
             uown[i][r] = f[r];
             sm.ub[(row >> 4) * 128 + r * 16 + (row & 15)] = (unsigned char)(signed char)(int)f[r];
           }
-          if (ok) {
-            int idx = 0;
-#pragma unroll
-            for (int j = 0; j < R; ++j)
-#pragma unroll
-              for (int r = j; r < R; ++r) gacc[idx++] += (int)f[j] * (int)f[r];
+          // ---- V-phase on the tensor core, issued per 32-row chunk as soon as the chunk is projected (the MMAs of
+          //      chunk i run under the Gauss–Seidel arithmetic of chunk i+1): D_a += S_a^T U, D_3 += U^T U ----
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // int8 U rows -> visible to the tensor core
+          __syncwarp();
+          if (lane == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int j = warp_u + i * NW;  // k-chunk of 32 rows: rows i*NT + 32*warp ..
+            const unsigned cbase = smem_u32(sm.ub) + j * 256;
+            const unsigned long long bd = umma_desc(cbase, 128, 128);
+            umma_i8_ts(tmem + kTcD1, tmem + j * 8, bd, idesc, 1);
+            umma_i8_ts(tmem + kTcD2, tmem + kTcColsA + j * 8, bd, idesc, 1);
+            // A = the same 8 x 32 int8 tile (stride 0 between the 8-row groups: accumulator lanes repeat mod 8)
+            umma_i8(tmem + kTcD3, umma_desc(cbase, 128, 0), bd, idesc_ss, 1);
+            if (i == RT - 1)
+              asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&sm.mma_done)) : "memory");
           }
+          __syncwarp();
         }
       }
-      // U^T U partial of this warp: exact integers, one REDUX per entry
-      {
-        int idx = 0;
+      TC_TRACE(3)
+      if (sweeps_done > 0) cluster_wait();  // every CTA has consumed the previous exchange (long satisfied)
+      if (warp < 4) {
+        // ---- epilogue: this sweep's sums = accumulator differences; Q.24 int64; reduce-scatter to the owners ----
+        if (tid == 0) {
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&sm.full)), "r"(2048 + cluster_size * 64) : "memory");
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&sm.vfull)), "r"(N * 16) : "memory");
+        }
+        mbar_wait(&sm.mma_done, mma_phase);
+        TC_TRACE(4)
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int l = warp * 32 + lane, a_lo = l & 1, n = l >> 1;
+        unsigned d1[4], d2[4], d3[4];
+        tmem_ld4(tmem + ((unsigned)(warp * 32) << 16) + kTcD1, d1);
+        tmem_ld4(tmem + ((unsigned)(warp * 32) << 16) + kTcD2, d2);
+        tmem_ld4(tmem + ((unsigned)(warp * 32) << 16) + kTcD3, d3);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        TC_TRACE(10)
+        long long tot[4];
+        int e3[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int e1 = (int)d1[r] - prev1[r], e2 = (int)d2[r] - prev2[r];  // exact mod 2^32
+          e3[r] = (int)d3[r] - prev3[r];
+          prev1[r] = (int)d1[r], prev2[r] = (int)d2[r], prev3[r] = (int)d3[r];
+          const long long mine = ((long long)e1 << (24 - 8 * a_lo)) + ((long long)e2 << (8 - 8 * a_lo));
+          tot[r] = mine + __shfl_xor_sync(0xffffffffu, mine, 1);  // all four slices of (n, r)
+        }
+        const long long p0 = a_lo ? tot[2] : tot[0], p1 = a_lo ? tot[3] : tot[1];
+        TC_TRACE(11)
+        const unsigned bar = smem_u32(&sm.full);
+        const int owner = n >> npr_log, n_local = n & (npr - 1);
+        push_2x64(map_to_rank(smem_u32(&sm.srecv[((crank << npr_log) + n_local) * 2 + a_lo]), owner), p0, p1,
+                  map_to_rank(bar, owner));
+        if (warp == 0) {  // U^T U row j = lane & 3 (accumulator lanes 0..3) to rank lane >> 2: one push per lane
+          int row3[4];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) row3[r] = __shfl_sync(0xffffffffu, e3[r], lane & 3);
+          const int cr = lane >> 2;
+          if (cr < cluster_size)
+            push_4x32(map_to_rank(smem_u32(&sm.grecv[crank * 4 + (lane & 3)]), cr), row3[0], row3[1], row3[2], row3[3],
+                      map_to_rank(bar, cr));
+        }
+      }
+      mma_phase ^= 1;
+      TC_TRACE(5)
+
+      // ---------------- V update of the owned rows, then all-gather ----------------
+      if (warp < 2 && warp * 32 < npr) {  // warps that own columns (warp 1 only when the cluster is a single CTA)
+        mbar_wait(&sm.full, full_phase);
+        TC_TRACE(6)
+        // U^T U of the whole matrix: lane e sums entry e over the ranks, then every lane collects the R x R block
+        int ge = 0;
+#pragma unroll
+        for (int cr = 0; cr < kTcMaxCluster; ++cr)
+          ge += (cr < cluster_size && lane < 16) ? reinterpret_cast<const int*>(sm.grecv)[cr * 16 + (lane & 15)] : 0;
+        float b2[R * R];
 #pragma unroll
         for (int j = 0; j < R; ++j)
 #pragma unroll
-          for (int r = j; r < R; ++r) {
-            const int g = __reduce_add_sync(0xffffffffu, gacc[idx++]);
-            if (lane == 0) sm.gred[warp * R * R + j * R + r] = g, sm.gred[warp * R * R + r * R + j] = g;
+          for (int r = 0; r < R; ++r) b2[j * R + r] = (float)__shfl_sync(0xffffffffu, ge, j * 4 + r);
+        float f[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        if (tid < npr) {
+          long long s[4] = {0, 0, 0, 0};
+#pragma unroll
+          for (int cr = 0; cr < kTcMaxCluster; ++cr) {
+            const bool on = cr < cluster_size;
+            const int slot = on ? ((cr << npr_log) + tid) * 2 : 0;
+            const longlong2 q0 = sm.srecv[slot], q1 = sm.srecv[slot + 1];
+            s[0] += on ? q0.x : 0, s[1] += on ? q0.y : 0, s[2] += on ? q1.x : 0, s[3] += on ? q1.y : 0;
           }
-      }
-      // ---------------- V-phase on the tensor core: D_a += S_a^T U over this warp's 2 x 32 rows ----------------
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // int8 U rows -> visible to the tensor core
-      __syncwarp();
-      if (lane == 0) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const unsigned bbase = smem_u32(sm.ub);
+          TC_TRACE(12)
+          const int n = crank * npr + tid;
+          float fr[R], A[R];
 #pragma unroll
-        for (int i = 0; i < RT; ++i) {
-          const int j = warp + i * NW;  // k-chunk of 32 rows: rows 32*warp.. (i = 0) and 384 + 32*warp.. (i = 1)
-          const unsigned long long bd = umma_desc(bbase + j * 256, 128, 128);
-          umma_i8_ts(tmem + kTcD1, tmem + j * 8, bd, idesc, 1);
-          umma_i8_ts(tmem + kTcD2, tmem + kTcColsA + j * 8, bd, idesc, 1);
-        }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&sm.mma_done)) : "memory");
-      }
-      if (warp < 4) {
-        mbar_wait(&sm.mma_done, mma_phase);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int l = warp * 32 + lane, a_lo = l >> 6;
-        unsigned d1[8], d2[8];
-        tmem_ld8(tmem + ((unsigned)(warp * 32) << 16) + kTcD1, d1);
-        tmem_ld8(tmem + ((unsigned)(warp * 32) << 16) + kTcD2, d2);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const double s1 = a_lo ? 0.00390625 : 1.0;                       // 2^(-8 a)
-        const double s2 = a_lo ? 5.9604644775390625e-08 : 1.52587890625e-05;  // 2^(-8 (a+2))
+          for (int r = 0; r < R; ++r) fr[r] = sm.v[n * R + r], A[r] = (float)((double)s[r] * 5.9604644775390625e-08);  // one rounding
+          gs_row<R>(fr, A, b2, t2_native_v, P.lo, P.hi);
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const int e1 = (int)d1[r] - prev1[r], e2 = (int)d2[r] - prev2[r];  // this sweep's sums (exact mod 2^32)
-          prev1[r] = (int)d1[r], prev2[r] = (int)d2[r];
-          sm.comb[l * 4 + r] = (double)e1 * s1 + (double)e2 * s2;
+          for (int r = 0; r < R; ++r) f[r] = fr[r];
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      }
-      mma_phase ^= 1;
-      __syncthreads();
-      for (int e = tid; e < N * R + R * R; e += NT) {
-        if (e < N * R) {
-          const int n = e / R, r = e - n * R;
-          sm.part[pbuf][e] = sm.comb[n * 4 + r] + sm.comb[(n + 64) * 4 + r];  // exact: <= 52 significant bits
+        // all-gather: (row k, rank c) pairs spread over the lanes — one or two pushes per lane instead of C per owner
+        const unsigned vbar = smem_u32(&sm.vfull);
+        if (npr > 32) {  // single-CTA cluster: every thread owns a row and keeps it local
+          push_4x32(map_to_rank(smem_u32(&sm.vrecv[tid]), 0), __float_as_int(f[0]), __float_as_int(f[1]), __float_as_int(f[2]),
+                    __float_as_int(f[3]), map_to_rank(vbar, 0));
         } else {
-          int g = 0;
 #pragma unroll
-          for (int w2 = 0; w2 < NW; ++w2) g += sm.gred[w2 * R * R + e - N * R];
-          sm.part[pbuf][e] = (double)g;
-        }
-      }
-
-      // ---------------- exchange partials across the cluster, every CTA sums in rank order ----------------
-      if (cluster_size > 1) {
-        cluster.sync();
-        for (int e = tid; e < N * R + R * R; e += NT) {
-          double s = 0.0;
-          for (int cr = 0; cr < cluster_size; ++cr) {
-            const double* remote = cluster.map_shared_rank(&sm.part[pbuf][0], cr);
-            s += remote[e];
+          for (int t = 0; t < 2; ++t) {
+            const int q = lane + 32 * t, k = q & (npr - 1), cr = q >> npr_log;
+            int w[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) w[r] = __shfl_sync(0xffffffffu, __float_as_int(f[r]), k);
+            if (cr < cluster_size)
+              push_4x32(map_to_rank(smem_u32(&sm.vrecv[crank * npr + k]), cr), w[0], w[1], w[2], w[3], map_to_rank(vbar, cr));
           }
-          if (e < N * R) sm.a2[e] = (float)s;
-          else sm.b2[e - N * R] = (float)s;
-        }
-      } else {
-        __syncthreads();
-        for (int e = tid; e < N * R + R * R; e += NT) {
-          if (e < N * R) sm.a2[e] = (float)sm.part[pbuf][e];
-          else sm.b2[e - N * R] = (float)sm.part[pbuf][e];
         }
       }
-      pbuf ^= 1;
-      __syncthreads();
-
-      // ---------------- V update (identical in every CTA of the cluster) and B = V^T V ----------------
-      for (int n = tid; n < N; n += NT) {
-        float f[R], A[R];
+      if (warp < 2) {
+        mbar_wait(&sm.vfull, full_phase);
+        TC_TRACE(13)
+        const float4 row = sm.vrecv[tid];
+        const float fv[4] = {row.x, row.y, row.z, row.w};
 #pragma unroll
-        for (int r = 0; r < R; ++r) f[r] = sm.v[n * R + r], A[r] = sm.a2[n * R + r];
-        gs_row<R>(f, A, sm.b2, t2_native_v, P.lo, P.hi);
+        for (int r = 0; r < R; ++r) sm.v[tid * R + r] = fv[r];
 #pragma unroll
-        for (int r = 0; r < R; ++r) sm.v[n * R + r] = f[r];
+        for (int j = 0; j < R; ++j)
+#pragma unroll
+          for (int r = j; r < R; ++r) {  // V is integer-valued now: exact
+            const int p = __reduce_add_sync(0xffffffffu, (int)fv[j] * (int)fv[r]);
+            if (lane == 0) sm.bi[warp][j * R + r] = p, sm.bi[warp][r * R + j] = p;
+          }
       }
+      full_phase ^= 1;
+      TC_TRACE(7)
       __syncthreads();
-      {
-        for (int e = warp; e < R * R; e += NW) {  // V is integer-valued: every order gives the same exact result
-          const int j = e / R, r = e - j * R;
-          float p = __fmaf_rn(sm.v[lane * R + j], sm.v[lane * R + r],
-                              __fmul_rn(sm.v[(lane + 32) * R + j], sm.v[(lane + 32) * R + r]));
-          for (int o = 16; o; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
-          if (lane == 0) sm.b[e] = p;
-        }
-      }
-      __syncthreads();
+      TC_TRACE(8)
+      cluster_arrive();  // this CTA is done with its receive buffers
+      ++sweeps_done;
     }
 
     // ---- write the factors of this CTA's rows (and V once per cluster) ----
+    TC_TRACE_S(7)
 #pragma unroll
     for (int i = 0; i < RT; ++i) {
       const int row = tid + i * NT;
@@ -388,7 +493,7 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
       }
     }
   }
-  if (cluster_size > 1) cluster.sync();  // nobody leaves while its partials may still be read
+  if (sweeps_done > 0) cluster_wait();  // all pushes have landed and were consumed: nobody is written to after exit
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));

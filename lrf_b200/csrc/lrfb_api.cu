@@ -298,18 +298,8 @@ int launch_bcd_tc_cfg(const BcdBatch& b, cudaStream_t st) {
   if (e != cudaSuccess) return fail((int)e, "bcd_tc launch: %s", cudaGetErrorString(e));
   return check_launch("bcd_tc_kernel");
 }
-int tc_variant() {
-  static int v = -1;  // dev knob: LRFB_TC_VARIANT=0 (768 rows x 384 threads, 1 CTA/SM) | 1 (384 x 192, 2 CTAs/SM)
-  if (v < 0) {
-    const char* e = getenv("LRFB_TC_VARIANT");
-    v = e ? atoi(e) : 0;
-  }
-  return v;
-}
 template <int R>
 int launch_bcd_tc(const BcdBatch& b, cudaStream_t st) {
-  if (tc_variant() == 1) return launch_bcd_tc_cfg<R, 384, 192>(b, st);
-  if (tc_variant() == 2) return launch_bcd_tc_cfg<R, 384, 128>(b, st);
   return launch_bcd_tc_cfg<R, 768, 384>(b, st);
 }
 bool tc_enabled() {
