@@ -190,4 +190,82 @@ frontend8_chroma_kernel(const unsigned char* __restrict__ images, float* __restr
   }
 }
 
+// Fused variant for H % 16 == 0 and W % 16 == 0 (no padding on any plane, 2 x 2 pooling windows): the image is
+// read ONCE for all three planes, and the patch rows are staged in shared memory so that global memory sees only
+// fully coalesced accesses.  A CTA owns a 16-row x 256-pixel tile: thread (cy, wp) reads the 2-row x 8-pixel strip
+// of the three channels (3 x 2 x 8-byte loads; a warp covers 256 contiguous bytes of an image row), produces its
+// 2 x 8 luma values and the 4 Cb / 4 Cr values pooled from the strip, and scatters them into the tile's patch
+// layout (patch stride 68 floats: conflict-free 16-byte stores).  The tile's 2 x 32 luma patches and 16 + 16 chroma
+// patches are each contiguous in X, so the write-out is plain consecutive float4 stores.  Same arithmetic,
+// operation for operation, as the kernels above.
+constexpr int kTilePatchStride = 68;
+__global__ void __launch_bounds__(256)
+frontend8_fused_kernel(const unsigned char* __restrict__ images, float* __restrict__ xy, float* __restrict__ xcb,
+                       float* __restrict__ xcr, FrontParams P) {
+  __align__(16) __shared__ float s_lum[2 * 32 * kTilePatchStride];
+  __align__(16) __shared__ float s_cb[16 * kTilePatchStride];
+  __align__(16) __shared__ float s_cr[16 * kTilePatchStride];
+  const PlaneGeom gl = P.g[0], gc = P.g[1];
+  const size_t hw = (size_t)P.H * P.W;
+  const int nbl = gl.nbw, nbc = gc.nbw;  // W/8 and W/16 patches per patch row
+  const int tid = threadIdx.x, wp = tid & 31, cy = tid >> 5;
+  const int y0 = blockIdx.y * 16, wp0 = blockIdx.x * 32;  // first image row / first luma patch column of the tile
+  const int n_lp = min(32, nbl - wp0), n_cp = n_lp >> 1;  // patches of this tile that exist
+  for (int im = blockIdx.z; im < P.n_img; im += gridDim.z) {
+    const unsigned char* img = images + (size_t)im * 3 * hw;
+    __syncthreads();  // previous image's write-out is done with the staging buffers
+    if (wp < n_lp) {
+      float sb[4] = {0.0f, 0.0f, 0.0f, 0.0f}, sr[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy) {
+        const int ly = 2 * cy + dy;
+        const size_t off = (size_t)(y0 + ly) * P.W + (size_t)(wp0 + wp) * 8;
+        const uint2 r = *reinterpret_cast<const uint2*>(img + off);
+        const uint2 gg = *reinterpret_cast<const uint2*>(img + hw + off);
+        const uint2 b = *reinterpret_cast<const uint2*>(img + 2 * hw + off);
+        const unsigned rw[2] = {r.x, r.y}, gw[2] = {gg.x, gg.y}, bw[2] = {b.x, b.y};
+        float lum[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            const int px = 2 * j + s;
+            const float fr = byte_of(rw[px >> 2], px & 3), fg = byte_of(gw[px >> 2], px & 3),
+                        fb = byte_of(bw[px >> 2], px & 3);
+            lum[px] = ycc_from(fr, fg, fb, 0);
+            sb[j] = __fadd_rn(sb[j], ycc_from(fr, fg, fb, 1));
+            sr[j] = __fadd_rn(sr[j], ycc_from(fr, fg, fb, 2));
+          }
+        }
+        float* d = &s_lum[((ly >> 3) * 32 + wp) * kTilePatchStride + (ly & 7) * 8];
+        *reinterpret_cast<float4*>(d) = make_float4(lum[0], lum[1], lum[2], lum[3]);
+        *reinterpret_cast<float4*>(d + 4) = make_float4(lum[4], lum[5], lum[6], lum[7]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        sb[j] = __fdiv_rn(__fdiv_rn(sb[j], 2.0f), 2.0f);
+        sr[j] = __fdiv_rn(__fdiv_rn(sr[j], 2.0f), 2.0f);
+      }
+      const int co = (wp >> 1) * kTilePatchStride + cy * 8 + (wp & 1) * 4;
+      *reinterpret_cast<float4*>(&s_cb[co]) = make_float4(sb[0], sb[1], sb[2], sb[3]);
+      *reinterpret_cast<float4*>(&s_cr[co]) = make_float4(sr[0], sr[1], sr[2], sr[3]);
+    }
+    __syncthreads();
+    // write-out: 2 runs of n_lp luma patches, 1 run of n_cp patches per chroma plane, all contiguous in X
+    float* oy = xy + (size_t)im * gl.rows * 64;
+    for (int i = tid; i < 2 * n_lp * 16; i += 256) {
+      const int pr = i / (n_lp * 16), rem = i - pr * n_lp * 16, patch = rem >> 4, q = rem & 15;
+      const float4 v = *reinterpret_cast<const float4*>(&s_lum[(pr * 32 + patch) * kTilePatchStride + q * 4]);
+      *reinterpret_cast<float4*>(oy + ((size_t)((y0 >> 3) + pr) * nbl + wp0 + patch) * 64 + q * 4) = v;
+    }
+    float* ocb = xcb + (size_t)im * gc.rows * 64;
+    float* ocr = xcr + (size_t)im * gc.rows * 64;
+    for (int i = tid; i < 2 * n_cp * 16; i += 256) {
+      const int pl = i / (n_cp * 16), rem = i - pl * n_cp * 16, patch = rem >> 4, q = rem & 15;
+      const float4 v = *reinterpret_cast<const float4*>(&(pl ? s_cr : s_cb)[patch * kTilePatchStride + q * 4]);
+      *reinterpret_cast<float4*>((pl ? ocr : ocb) + ((size_t)(y0 >> 4) * nbc + (wp0 >> 1) + patch) * 64 + q * 4) = v;
+    }
+  }
+}
+
 }  // namespace lrfb

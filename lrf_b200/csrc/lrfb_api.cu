@@ -516,9 +516,21 @@ bool fast8_geometry(const Geometry& g, const void* base) {
          ((uintptr_t)base % 16) == 0;
 }
 
+// one pass over the image for all three planes: additionally H % 16 == 0 and chroma exactly half height (no padding)
+bool fused8_geometry(const lrfb_qmf_config* cfg, const Geometry& g, const void* base) {
+  const FrontParams& f = g.fp;
+  return cfg->input_dtype == LRFB_U8 && fast8_geometry(g, base) && f.H % 16 == 0 && f.g[1].h * 2 == f.H &&
+         f.g[0].hp == f.H && f.g[1].hp * 2 == f.H && g.lay.n_planes == 3;
+}
+
 // planes: bit 0 = plane 0 (luma / RGB), bit 1 = planes 1 and 2 (chroma)
 int run_frontend(const lrfb_qmf_config* cfg, const Geometry& g, int batch, const void* d_images,
                  float* const* xs, cudaStream_t st, int planes = 3) {
+  if (planes == 3 && fused8_geometry(cfg, g, d_images)) {
+    dim3 grid((unsigned)((g.fp.g[0].nbw + 31) / 32), (unsigned)(g.fp.H / 16), (unsigned)std::min(batch, 65535));
+    LRFB_LAUNCH(frontend8_fused_kernel, grid, dim3(256), 0, st, (const unsigned char*)d_images, xs[0], xs[1], xs[2], g.fp);
+    return check_launch("frontend8_fused_kernel");
+  }
   if (cfg->input_dtype == LRFB_U8 && fast8_geometry(g, d_images)) {
     const unsigned char* img = (const unsigned char*)d_images;
     if (planes & 1) {
@@ -647,11 +659,18 @@ LRFB_EXPORT int32_t lrfb_qmf_encode(const lrfb_qmf_config* cfg, int32_t batch, c
     bool chains = !getenv("LRFB_NO_CHAIN_OVERLAP");
     for (int pl = 0; pl < 3 && chains; ++pl) chains = FactorWs::gram_split(batch, L.rows[pl]) == 1;
     if (chains) {
-      cudaEventRecord(side->fork, st);  // orders the helper stream after whatever produced d_images
-      cudaStreamWaitEvent(side->stream, side->fork, 0);
-      if ((rc = run_frontend(cfg, g, batch, d_images, xs, st, 1))) return rc;
-      if ((rc = run_plane(0, 0, st))) return rc;
-      if ((rc = run_frontend(cfg, g, batch, d_images, xs, side->stream, 2))) return rc;
+      if (fused8_geometry(cfg, g, d_images)) {  // the image is read once; the chroma chain forks after it
+        if ((rc = run_frontend(cfg, g, batch, d_images, xs, st, 3))) return rc;
+        cudaEventRecord(side->fork, st);
+        cudaStreamWaitEvent(side->stream, side->fork, 0);
+        if ((rc = run_plane(0, 0, st))) return rc;
+      } else {
+        cudaEventRecord(side->fork, st);  // orders the helper stream after whatever produced d_images
+        cudaStreamWaitEvent(side->stream, side->fork, 0);
+        if ((rc = run_frontend(cfg, g, batch, d_images, xs, st, 1))) return rc;
+        if ((rc = run_plane(0, 0, st))) return rc;
+        if ((rc = run_frontend(cfg, g, batch, d_images, xs, side->stream, 2))) return rc;
+      }
       if ((rc = run_plane(1, 0, side->stream))) return rc;
       if ((rc = run_plane(2, 0, side->stream))) return rc;
     } else {
