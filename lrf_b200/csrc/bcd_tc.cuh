@@ -22,7 +22,7 @@
 namespace lrfb {
 
 constexpr int kTcRows = 768;       // largest row slice per CTA
-constexpr int kTcMaxCluster = 8;   // portable cluster size
+constexpr int kTcMaxCluster = 16;  // 8 for the 768-row shape (portable), 16 for the 384-row shape (non-portable)
 // Per-sweep exchange — no cluster barrier and no all-to-all of the partial sums on the critical path (DSMEM moves
 // only ~20 B/cycle/SM, so a 2 KB x 8 all-to-all alone costs ~750 cycles):
 //   1. reduce-scatter: rank c OWNS the 64/C columns n in [c*64/C, (c+1)*64/C).  After the tensor core has finished a
@@ -48,6 +48,7 @@ struct TcSmem {
   alignas(16) float4 vrecv[N];          // gathered new rows of V (padded to 4 columns)
   unsigned long long mma_done, clear_done, full, vfull;
   unsigned tmem_base;
+  int next_mat;                         // rank 0: matrix index drawn for the whole cluster
 };
 
 __device__ __forceinline__ void tmem_st16(unsigned taddr, const unsigned (&v)[16]) {
@@ -100,22 +101,26 @@ __device__ __forceinline__ void umma_i8_ts(unsigned tmem_d, unsigned tmem_a, uns
 #ifdef LRFB_TC_TRACE
 __device__ long long g_tc_trace[16 * 12];  // probe build only (tools/probes/tc_trace.cu): clock64 at 9 points of every sweep
 #define TC_TRACE(pt) \
-  if (blockIdx.x == 0 && tid == 0 && mat == cluster_id && it < 12) g_tc_trace[(pt) * 12 + it] = clock64();
+  if (blockIdx.x == 0 && tid == 0 && mats_seen == 1 && it < 12) g_tc_trace[(pt) * 12 + it] = clock64();
 #define TC_TRACE_S(pt) \
-  if (blockIdx.x == 0 && tid == 0 && mat == cluster_id + n_clusters) g_tc_trace[14 * 12 + (pt)] = clock64();
+  if (blockIdx.x == 0 && tid == 0 && mats_seen == 2) g_tc_trace[14 * 12 + (pt)] = clock64();
 #else
 #define TC_TRACE(pt)
 #define TC_TRACE_S(pt)
 #endif
 
 template <int R, int ROWS, int NT>
-__global__ void __launch_bounds__(NT, (ROWS <= 384 ? 2 : 1))  // 2 CTAs/SM: the tail of one overlaps the other's compute
+// 384-row shape: 2 CTAs per SM, so the exchange latency of one overlaps the arithmetic of the other.  Its 6 warps land
+// 2,2,1,1 on the four scheduler partitions, so two CTAs put 4 warps on one partition's 16K registers: <= 128 registers
+// per thread (bound declared as 256 threads x 2 CTAs).
+__global__ void __launch_bounds__((ROWS <= 384 ? 256 : NT), (ROWS <= 384 ? 2 : 1))
 bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
   constexpr int N = 64, RT = ROWS / NT, NW = NT / 32;
   constexpr int kTcRows = ROWS;
   constexpr int kTcColsA = ROWS / 4;                        // TMEM columns per A block (4 rows per cell)
   constexpr int kTcD1 = 2 * kTcColsA + 16, kTcD2 = kTcD1 + 16, kTcD3 = kTcD2 + 16;  // accumulator columns
   constexpr int kTmemCols = ROWS > 384 ? 512 : 256;
+  constexpr int kMaxC = ROWS > 384 ? 8 : 16;  // largest cluster this shape is launched with
   static_assert(ROWS % NT == 0 && ROWS % 64 == 0 && NW >= 4 && kTcD3 + 8 <= kTmemCols, "shape");
   using S = TcSmem<R, ROWS, NT>;
   LRFB_DYN_SMEM(smem_raw);
@@ -125,8 +130,6 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
   const int M = P.M;
   cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
   const int crank = (int)cluster.block_rank();
-  const int cluster_id = blockIdx.x / cluster_size;
-  const int n_clusters = gridDim.x / cluster_size;
   const bool t2_native_u = bmm_native(R - 1, M, 1);
   constexpr bool t2_native_v = (long long)(R - 1) * N < 400;
   const bool from_a = P.s0 != nullptr;
@@ -135,6 +138,9 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
   unsigned mma_phase = 0, full_phase = 0;
   const int npr = N / cluster_size, npr_log = 6 - (31 - __clz(cluster_size));  // columns of V owned per rank
   int sweeps_done = 0;
+#ifdef LRFB_TC_TRACE
+  int mats_seen = 0;
+#endif
 
   if (tid == 0) {
     mbar_init(&sm.mma_done, NW);  // one tcgen05.commit per warp and sweep
@@ -174,9 +180,19 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   cluster.sync();  // every peer's mbarriers are initialised before anyone pushes
 
-  for (int mat = cluster_id; mat < P.n_mat; mat += n_clusters) {
+  for (;;) {
+    // ---- rank 0 draws the next matrix for the cluster ----
+    if (sweeps_done > 0) cluster_wait();  // balance the last sweep's arrive: every exchange buffer is idle
+    sweeps_done = 0;
+    if (crank == 0 && tid == 0) sm.next_mat = atomicAdd(P.work_counter, 1);
+    cluster.sync();
+    const int mat = *cluster.map_shared_rank(&sm.next_mat, 0);
+    if (mat >= P.n_mat) break;  // uniform over the cluster
     const float* X = P.X + (size_t)mat * P.x_stride;
     float* V = P.V + (size_t)mat * N * R;
+#ifdef LRFB_TC_TRACE
+    ++mats_seen;
+#endif
 
     // ---- load this CTA's slice of X once (swizzled f32) and V ----
     TC_TRACE_S(0)
@@ -189,15 +205,6 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
       else dst[0] = dst[1] = dst[2] = dst[3] = 0.0f;
     }
     cp_async_commit();
-    // pull this CTA's slice of the NEXT matrix into L2 while HBM is otherwise idle during the sweeps
-#ifndef LRFB_TC_NO_PREFETCH
-    if (mat + n_clusters < P.n_mat && rows_here > 0) {
-      const char* nx = reinterpret_cast<const char*>(P.X + (size_t)(mat + n_clusters) * P.x_stride + (size_t)row0 * N);
-      const int bytes = rows_here * N * 4;
-      for (int o = tid * 4096; o < bytes; o += NT * 4096)
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nx + o), "r"(min(4096, bytes - o)) : "memory");
-    }
-#endif
     for (int i = tid; i < N * R; i += NT) sm.v[i] = V[i];
     if (tid < R) {
       float inv = 0.0f;
@@ -248,7 +255,7 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
     }
     TC_TRACE_S(5)
     // the first kReg A-phase rows of this thread stay in registers for all sweeps
-    constexpr int kReg = (NT == 128) ? 2 : (R == 4 ? 1 : 0);
+    constexpr int kReg = (ROWS <= 384) ? 0 : (R == 4 ? 1 : 0);  // the 2-CTAs-per-SM shape must stay within 128 registers
     constexpr int kRegN = kReg ? N : 1;
     float xr[kReg ? kReg : 1][kRegN];
 #pragma unroll
@@ -391,10 +398,13 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
           int row3[4];
 #pragma unroll
           for (int r = 0; r < 4; ++r) row3[r] = __shfl_sync(0xffffffffu, e3[r], lane & 3);
-          const int cr = lane >> 2;
-          if (cr < cluster_size)
-            push_4x32(map_to_rank(smem_u32(&sm.grecv[crank * 4 + (lane & 3)]), cr), row3[0], row3[1], row3[2], row3[3],
-                      map_to_rank(bar, cr));
+#pragma unroll
+          for (int t = 0; t < kMaxC / 8; ++t) {
+            const int cr = (lane >> 2) + 8 * t;
+            if (cr < cluster_size)
+              push_4x32(map_to_rank(smem_u32(&sm.grecv[crank * 4 + (lane & 3)]), cr), row3[0], row3[1], row3[2], row3[3],
+                        map_to_rank(bar, cr));
+          }
         }
       }
       mma_phase ^= 1;
@@ -407,7 +417,7 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
         // U^T U of the whole matrix: lane e sums entry e over the ranks, then every lane collects the R x R block
         int ge = 0;
 #pragma unroll
-        for (int cr = 0; cr < kTcMaxCluster; ++cr)
+        for (int cr = 0; cr < kMaxC; ++cr)
           ge += (cr < cluster_size && lane < 16) ? reinterpret_cast<const int*>(sm.grecv)[cr * 16 + (lane & 15)] : 0;
         float b2[R * R];
 #pragma unroll
@@ -418,7 +428,7 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
         if (tid < npr) {
           long long s[4] = {0, 0, 0, 0};
 #pragma unroll
-          for (int cr = 0; cr < kTcMaxCluster; ++cr) {
+          for (int cr = 0; cr < kMaxC; ++cr) {
             const bool on = cr < cluster_size;
             const int slot = on ? ((cr << npr_log) + tid) * 2 : 0;
             const longlong2 q0 = sm.srecv[slot], q1 = sm.srecv[slot + 1];
@@ -493,7 +503,7 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
       }
     }
   }
-  if (sweeps_done > 0) cluster_wait();  // all pushes have landed and were consumed: nobody is written to after exit
+  // (the loop exits right after a cluster.sync that followed the last exchange: nobody is written to after exit)
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));

@@ -148,7 +148,7 @@ int make_map(const Geometry& g, int batch, lrfb_qmf_workspace_map* m) {
     m->evec[pl] = off;
     off = align_up(off + (int64_t)batch * L.cols * L.rank[pl] * 8, 256);
     m->sigma[pl] = off;
-    off = align_up(off + (int64_t)batch * L.rank[pl] * 12, 256);
+    off = align_up(off + (int64_t)batch * L.rank[pl] * 12 + 16, 256);  // f64 + f32 singular values, work counter
   }
   m->total_bytes = off;
   return 0;
@@ -271,17 +271,26 @@ int launch_bcd_tc_cfg(const BcdBatch& b, cudaStream_t st) {
     if (e != cudaSuccess) return fail((int)e, "non-portable cluster size: %s", cudaGetErrorString(e));
   }
   cudaLaunchConfig_t cfg = {};
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = csize, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-  cfg.blockDim = dim3(NT), cfg.dynamicSmemBytes = smem, cfg.stream = st, cfg.attrs = attr, cfg.numAttrs = 1;
+  // 2 CTAs per SM only pay off when they belong to DIFFERENT clusters (CTAs of one cluster move in lock-step)
+  attr[1].id = cudaLaunchAttributeClusterSchedulingPolicyPreference;
+  attr[1].val.clusterSchedulingPolicyPreference = cudaClusterSchedulingPolicySpread;
+  static const int policy = getenv("LRFB_TC_POLICY") ? atoi(getenv("LRFB_TC_POLICY")) : 1;
+  attr[1].val.clusterSchedulingPolicyPreference = (cudaClusterSchedulingPolicy)policy;
+  cfg.blockDim = dim3(NT), cfg.dynamicSmemBytes = smem, cfg.stream = st, cfg.attrs = attr;
+  cfg.numAttrs = (ROWS <= 384 && csize > 1) ? 2 : 1;
   cfg.gridDim = dim3(csize);
   int max_clusters = 0;
   e = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
   if (e != cudaSuccess || max_clusters < 1) {
     cudaGetLastError();
-    max_clusters = std::max(1, num_sms() * (ROWS <= 384 ? 2 : 1) / csize);
+    max_clusters = std::max(1, num_sms() / csize);
   }
+  // the occupancy calculation assumes one CTA per SM for any kernel that allocates tensor memory; two 384-row CTAs do
+  // share an SM (tools/probes/occ_probe.cu).  Clusters that find no SM pair start late and find no work left.
+  if (ROWS <= 384) max_clusters *= 2;
   if (const char* ov = getenv("LRFB_TC_CLUSTERS")) max_clusters = std::max(1, atoi(ov) * 8 / csize);  // dev knob (per 8-CTA unit)
   cfg.gridDim = dim3((unsigned)(std::min(b.n_mat, max_clusters) * csize));
   if (getenv("LRFB_DEBUG")) {
@@ -298,8 +307,17 @@ int launch_bcd_tc_cfg(const BcdBatch& b, cudaStream_t st) {
   if (e != cudaSuccess) return fail((int)e, "bcd_tc launch: %s", cudaGetErrorString(e));
   return check_launch("bcd_tc_kernel");
 }
+int tc_variant() {
+  static int v = -1;  // dev knob: LRFB_TC_VARIANT=0 (768 rows x 384 threads, 1 CTA/SM) | 1 (384 x 192, 2 CTAs/SM)
+  if (v < 0) {
+    const char* e = getenv("LRFB_TC_VARIANT");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
 template <int R>
 int launch_bcd_tc(const BcdBatch& b, cudaStream_t st) {
+  if (tc_variant() == 1 || (tc_variant() == 2 && R <= 2)) return launch_bcd_tc_cfg<R, 384, 192>(b, st);
   return launch_bcd_tc_cfg<R, 768, 384>(b, st);
 }
 bool tc_enabled() {
@@ -342,9 +360,14 @@ bool resident_ok(int N, int R, int M) {
 #endif
 }
 
-int run_bcd(const BcdBatch& b, int N, int R, float* bwork, cudaStream_t st) {
+// `counter`: 4 bytes of device memory private to this call (the tensor-core kernel hands out matrices dynamically)
+int run_bcd(const BcdBatch& b0, int N, int R, float* bwork, cudaStream_t st, int* counter) {
+  BcdBatch b = b0;
+  b.work_counter = counter;
 #ifndef LRFB_SIM
   if (resident_ok(N, R, b.M) && b.x_u8_range && tc_enabled() && b.M <= 8 * kTcRows) {
+    cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(int), st);
+    if (e != cudaSuccess) return fail((int)e, "work counter reset: %s", cudaGetErrorString(e));
     switch (R) {
       case 1: return launch_bcd_tc<1>(b, st);
       case 2: return launch_bcd_tc<2>(b, st);
@@ -475,14 +498,14 @@ int factorize_batch(const float* x, int n_mat, int M, int N, int R, float lo, fl
   b.s0 = s0;
   b.x_u8_range = x_in_u8_range ? 1 : 0;
   if (iters <= 0) return fail(LRFB_E_UNSUPPORTED, "num_iters must be >= 1");
-  return run_bcd(b, N, R, bwork, st);
+  return run_bcd(b, N, R, bwork, st, reinterpret_cast<int*>(reinterpret_cast<char*>(sigma) + (size_t)n_mat * R * 12));
 }
 
 #ifndef LRFB_SIM
 // Helper stream per device so the chroma sweeps can fill the SMs the luma clusters leave idle.
 struct SideStream {
-  cudaStream_t stream = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr, init2 = nullptr;
 };
 SideStream* side_stream() {
   static SideStream table[64];
@@ -494,6 +517,8 @@ SideStream* side_stream() {
     int least = 0, greatest = 0;
     cudaDeviceGetStreamPriorityRange(&least, &greatest);
     if (cudaStreamCreateWithPriority(&s.stream, cudaStreamNonBlocking, least) != cudaSuccess) return nullptr;
+    if (cudaStreamCreateWithPriority(&s.stream2, cudaStreamNonBlocking, least) != cudaSuccess) return nullptr;
+    cudaEventCreateWithFlags(&s.init2, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming);
   }
@@ -659,20 +684,49 @@ LRFB_EXPORT int32_t lrfb_qmf_encode(const lrfb_qmf_config* cfg, int32_t batch, c
     bool chains = !getenv("LRFB_NO_CHAIN_OVERLAP");
     for (int pl = 0; pl < 3 && chains; ++pl) chains = FactorWs::gram_split(batch, L.rows[pl]) == 1;
     if (chains) {
-      if (fused8_geometry(cfg, g, d_images)) {  // the image is read once; the chroma chain forks after it
+      // Three initialisation chains (Gram + eigen-solver: the latter latency-bound) run side by side; then the luma
+      // sweeps take their 15 clusters x 8 SMs and the chroma sweeps (Cb, then Cr) the SMs that leaves free.
+      if (fused8_geometry(cfg, g, d_images)) {  // the image is read once; the chroma chains fork after it
         if ((rc = run_frontend(cfg, g, batch, d_images, xs, st, 3))) return rc;
         cudaEventRecord(side->fork, st);
         cudaStreamWaitEvent(side->stream, side->fork, 0);
-        if ((rc = run_plane(0, 0, st))) return rc;
       } else {
-        cudaEventRecord(side->fork, st);  // orders the helper stream after whatever produced d_images
+        cudaEventRecord(side->fork, st);  // orders the helper streams after whatever produced d_images
         cudaStreamWaitEvent(side->stream, side->fork, 0);
         if ((rc = run_frontend(cfg, g, batch, d_images, xs, st, 1))) return rc;
-        if ((rc = run_plane(0, 0, st))) return rc;
         if ((rc = run_frontend(cfg, g, batch, d_images, xs, side->stream, 2))) return rc;
+        cudaEventRecord(side->fork, side->stream);
       }
-      if ((rc = run_plane(1, 0, side->stream))) return rc;
-      if ((rc = run_plane(2, 0, side->stream))) return rc;
+      cudaStreamWaitEvent(side->stream2, side->fork, 0);
+      static const bool timeline = getenv("LRFB_TIMELINE") != nullptr;  // dev aid: when does each chain finish?
+      cudaEvent_t ev[8] = {};
+      if (timeline) {
+        for (auto& e : ev) cudaEventCreate(&e);
+        cudaEventRecord(ev[0], st);
+      }
+      if ((rc = run_plane(0, 1, st))) return rc;
+      if (timeline) cudaEventRecord(ev[1], st);
+      if ((rc = run_plane(1, 1, side->stream))) return rc;
+      if (timeline) cudaEventRecord(ev[2], side->stream);
+      if ((rc = run_plane(2, 1, side->stream2))) return rc;
+      cudaEventRecord(side->init2, side->stream2);
+      if (timeline) cudaEventRecord(ev[3], side->stream2);
+      if ((rc = run_plane(0, 2, st))) return rc;
+      if (timeline) cudaEventRecord(ev[4], st);
+      if ((rc = run_plane(1, 2, side->stream))) return rc;
+      if (timeline) cudaEventRecord(ev[5], side->stream);
+      cudaStreamWaitEvent(side->stream, side->init2, 0);
+      if ((rc = run_plane(2, 2, side->stream))) return rc;
+      if (timeline) {
+        cudaEventRecord(ev[6], side->stream);
+        cudaStreamSynchronize(side->stream);
+        cudaStreamSynchronize(st);
+        float t[7] = {};
+        for (int i = 1; i < 7; ++i) cudaEventElapsedTime(&t[i], ev[0], ev[i]);
+        fprintf(stderr, "[lrfb timeline, ms after the front end] init: luma %.2f cb %.2f cr %.2f | sweeps: luma %.2f cb %.2f cr %.2f\n",
+                t[1], t[2], t[3], t[4], t[5], t[6]);
+        for (auto& e : ev) cudaEventDestroy(e);
+      }
     } else {
       if ((rc = run_frontend(cfg, g, batch, d_images, xs, st))) return rc;
       for (int pl = 0; pl < 3; ++pl)
@@ -698,7 +752,7 @@ LRFB_EXPORT int32_t lrfb_qmf_encode(const lrfb_qmf_config* cfg, int32_t batch, c
 LRFB_EXPORT int64_t lrfb_factorize_workspace_bytes(int32_t n_mat, int32_t M, int32_t N, int32_t R) {
   if (n_mat <= 0 || M <= 0 || N <= 0 || R <= 0) return 0;
   return align_up((int64_t)n_mat * N * N * 8, 256) + align_up((int64_t)n_mat * N * R * 8, 256) +
-         align_up((int64_t)n_mat * R * 12, 256) + FactorWs::bytes(n_mat, M, N, R);
+         align_up((int64_t)n_mat * R * 12 + 16, 256) + FactorWs::bytes(n_mat, M, N, R);
 }
 
 LRFB_EXPORT int32_t lrfb_factorize(const float* d_x, int32_t n_mat, int32_t M, int32_t N, int32_t R,
@@ -718,7 +772,7 @@ LRFB_EXPORT int32_t lrfb_factorize(const float* d_x, int32_t n_mat, int32_t M, i
   double* evec = reinterpret_cast<double*>(ws);
   ws += align_up((int64_t)n_mat * N * R * 8, 256);
   double* sigma = reinterpret_cast<double*>(ws);
-  ws += align_up((int64_t)n_mat * R * 12, 256);
+  ws += align_up((int64_t)n_mat * R * 12 + 16, 256);
   return factorize_batch(d_x, n_mat, M, N, R, bound_lo, bound_hi, num_iters, d_u, d_v, nullptr, nullptr, 0,
                          d_init_u, d_init_v, d_sign_flip, gram, evec, sigma, ws, 0,
                          (cudaStream_t)(uintptr_t)stream);
@@ -742,7 +796,9 @@ LRFB_EXPORT int32_t lrfb_bcd(const float* d_x, int32_t n_mat, int32_t M, int32_t
   b.s0 = d_s0;
   b.x_u8_range = (flags & 1u) ? 1 : 0;
   b.M = M, b.n_mat = n_mat, b.num_iters = num_iters, b.lo = ceilf(bound_lo), b.hi = floorf(bound_hi);
-  return run_bcd(b, N, R, reinterpret_cast<float*>(d_workspace), (cudaStream_t)(uintptr_t)stream);
+  // the generic kernel's scratch is unused whenever the counter is (tensor-core path): they may share the buffer
+  return run_bcd(b, N, R, reinterpret_cast<float*>(d_workspace), (cudaStream_t)(uintptr_t)stream,
+                 reinterpret_cast<int*>(d_workspace));
 }
 
 LRFB_EXPORT int32_t lrfb_ffma_probe(float* d_out, int32_t iters, void* stream) {

@@ -6,7 +6,7 @@
 #include <vector>
 #include <random>
 using namespace lrfb;
-int main() {
+int main(int argc, char** argv) {
   const int B = 240, M = 6144, N = 64, R = 4;
   std::vector<float> hx((size_t)B * M * N), hv((size_t)B * N * R), hu((size_t)B * M * R);
   std::mt19937 rng(1);
@@ -22,16 +22,24 @@ int main() {
   BcdBatch b = {};
   b.X = X, b.x_stride = (long long)M * N, b.U = U, b.V = V, b.M = M, b.n_mat = B, b.num_iters = 10, b.lo = -16, b.hi = 15;
   b.x_u8_range = 1;
-  auto kern = bcd_tc_kernel<4, 768, 384>;
-  const size_t smem = sizeof(TcSmem<4, 768, 384>);
+  int* counter;
+  cudaMalloc(&counter, 4);
+  b.work_counter = counter;
+  const bool small = argc > 1 && atoi(argv[1]) == 1;  // 1: 384 rows x 192 threads, clusters of 16, 2 CTAs per SM
+  auto kern = small ? bcd_tc_kernel<4, 384, 192> : bcd_tc_kernel<4, 768, 384>;
+  const size_t smem = small ? sizeof(TcSmem<4, 384, 192>) : sizeof(TcSmem<4, 768, 384>);
+  const int csize = small ? 16 : 8, nt = small ? 192 : 384, rows = small ? 384 : 768;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 8, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-  cfg.blockDim = dim3(384), cfg.dynamicSmemBytes = smem, cfg.attrs = attr, cfg.numAttrs = 1, cfg.gridDim = dim3(120);
+  attr[0].val.clusterDim.x = csize, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(nt), cfg.dynamicSmemBytes = smem, cfg.attrs = attr, cfg.numAttrs = 1, cfg.gridDim = dim3(small ? 224 : 120);
   for (int rep = 0; rep < 2; ++rep) {
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, b, 8, 768);
+    cudaMemset(counter, 0, 4);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, b, csize, rows);
     cudaError_t e2 = cudaDeviceSynchronize();
     if (e != cudaSuccess || e2 != cudaSuccess) { printf("error %s %s\n", cudaGetErrorString(e), cudaGetErrorString(e2)); return 1; }
   }
