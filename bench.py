@@ -165,7 +165,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="images per GPU per step")
     ap.add_argument("--ref-images", type=int, default=32, help="images per step for --impl reference")
-    ap.add_argument("--cpu-sample", type=int, default=96, help="images for the cpu_baseline leg")
+    ap.add_argument("--cpu-sample", type=int, default=512, help="images for the cpu_baseline leg")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -304,7 +304,7 @@ def main():
         with open(tp) as f:
             traffic = json.load(f)["bytes_per_image"] * B
     achieved_gbs = alg_bytes / (bcd_ms / 1e3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "bcd_resident_kernel<4,768,384>: all 10 BCD sweeps on the luma planes (lrfb_bcd)", "achieved": achieved_gbs,
+    roofline = {"bound": "hbm", "kernel": "bcd_tc_kernel<4,768,384>: all 10 BCD sweeps on the luma planes (lrfb_bcd)", "achieved": achieved_gbs,
                 "peak": peaks["hbm_gbs"], "peak_source": peak_src, "unit": "GB/s",
                 "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": traffic,
                 "ms_per_launch": bcd_ms, "algorithmic_bytes_per_launch": alg_bytes,

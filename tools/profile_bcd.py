@@ -1,5 +1,5 @@
 """Dev tool: launch only the dominant kernel (BCD sweeps on the luma planes, via lrfb_bcd) at bench.py's
-configuration, for `ncu --set full -k regex:bcd_resident` captures (profiles/)."""
+configuration, for `ncu --set full -k regex:bcd_tc` captures (profiles/)."""
 import ctypes as C
 import os
 import sys
