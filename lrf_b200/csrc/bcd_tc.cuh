@@ -88,6 +88,18 @@ __device__ __forceinline__ void push_4x32(unsigned remote, int a, int b, int c, 
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
+// two independent single-rounded FMAs in one issue slot (FFMA2 with a broadcast scalar operand): bit-identical to
+// fmaf(x, b.x, c.x) and fmaf(x, b.y, c.y)
+__device__ __forceinline__ float2 ffma2_bcast(float x, float2 b, float2 c) {
+  const float2 a = make_float2(x, x);
+  unsigned long long rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(rd)
+      : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)),
+        "l"(*reinterpret_cast<const unsigned long long*>(&c)));
+  return *reinterpret_cast<float2*>(&rd);
+}
+
 __device__ __forceinline__ void umma_i8_ts(unsigned tmem_d, unsigned tmem_a, unsigned long long b, unsigned idesc,
                                            unsigned accumulate) {
   asm volatile(
@@ -255,7 +267,8 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
     }
     TC_TRACE_S(5)
     // the first kReg A-phase rows of this thread stay in registers for all sweeps
-    constexpr int kReg = (ROWS <= 384) ? 0 : (R == 4 ? 1 : 0);  // the 2-CTAs-per-SM shape must stay within 128 registers
+    // the 2-CTAs-per-SM shape must stay within 128 registers; 256 threads x 3 rows have room for two register rows
+    constexpr int kReg = (ROWS <= 384) ? 0 : (NT == 256 ? 2 : (R == 4 ? 1 : 0));
     constexpr int kRegN = kReg ? N : 1;
     float xr[kReg ? kReg : 1][kRegN];
 #pragma unroll
@@ -278,6 +291,49 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
       TC_TRACE(0)
       {
         float acc[RT][R];
+        if (R % 2 == 0) {
+          // packed chains: each FFMA2 advances two of the R ascending-k chains of a row
+          constexpr int RP = R / 2 > 0 ? R / 2 : 1;
+          float2 acc2[RT][RP];
+#pragma unroll
+          for (int i = 0; i < RT; ++i)
+#pragma unroll
+            for (int r = 0; r < RP; ++r) acc2[i][r] = make_float2(0.0f, 0.0f);
+#pragma unroll
+          for (int k4 = 0; k4 < N / 4; ++k4) {
+            float2 vk[4][RP];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+              for (int r = 0; r < RP; ++r) vk[k][r] = *reinterpret_cast<const float2*>(&sm.v[(k4 * 4 + k) * R + 2 * r]);
+#pragma unroll
+            for (int i = 0; i < RT; ++i) {
+              const int row = tid + i * NT;
+              float4 xv;
+              if (i < kReg) {
+                constexpr int z = 0;
+                const int ii = i < kReg ? i : z;
+                xv = make_float4(xr[ii][(4 * k4 + 0) % kRegN], xr[ii][(4 * k4 + 1) % kRegN],
+                                 xr[ii][(4 * k4 + 2) % kRegN], xr[ii][(4 * k4 + 3) % kRegN]);
+              } else {
+                xv = *reinterpret_cast<const float4*>(&sm.x[row * N + ((k4 ^ (row & 7)) << 2)]);
+              }
+#pragma unroll
+              for (int r = 0; r < RP; ++r) {
+                float2 a = acc2[i][r];
+                a = ffma2_bcast(xv.x, vk[0][r], a);
+                a = ffma2_bcast(xv.y, vk[1][r], a);
+                a = ffma2_bcast(xv.z, vk[2][r], a);
+                a = ffma2_bcast(xv.w, vk[3][r], a);
+                acc2[i][r] = a;
+              }
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < RT; ++i)
+#pragma unroll
+            for (int r = 0; r < RP; ++r) acc[i][(2 * r) % R] = acc2[i][r].x, acc[i][(2 * r + 1) % R] = acc2[i][r].y;
+        } else {
 #pragma unroll
         for (int i = 0; i < RT; ++i)
 #pragma unroll
@@ -311,6 +367,7 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
               acc[i][r] = a;
             }
           }
+        }
         }
         TC_TRACE(1)
         float breg[R * R];  // V^T V: float chain of the initialisation in the first sweep, exact integers afterwards

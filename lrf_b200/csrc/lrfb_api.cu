@@ -318,6 +318,7 @@ int tc_variant() {
 template <int R>
 int launch_bcd_tc(const BcdBatch& b, cudaStream_t st) {
   if (tc_variant() == 1 || (tc_variant() == 2 && R <= 2)) return launch_bcd_tc_cfg<R, 384, 192>(b, st);
+  if (tc_variant() == 3 || (tc_variant() == 4 && R == 4)) return launch_bcd_tc_cfg<R, 768, 256>(b, st);
   return launch_bcd_tc_cfg<R, 768, 384>(b, st);
 }
 bool tc_enabled() {
