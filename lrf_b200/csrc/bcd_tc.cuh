@@ -472,10 +472,16 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
         mbar_wait(&sm.full, full_phase);
         TC_TRACE(6)
         // U^T U of the whole matrix: lane e sums entry e over the ranks, then every lane collects the R x R block
+        // (unconditional loads from clamped slots, masked afterwards: all loads in flight at once, no branches)
         int ge = 0;
+        {
+          int gv[kMaxC];
 #pragma unroll
-        for (int cr = 0; cr < kMaxC; ++cr)
-          ge += (cr < cluster_size && lane < 16) ? reinterpret_cast<const int*>(sm.grecv)[cr * 16 + (lane & 15)] : 0;
+          for (int cr = 0; cr < kMaxC; ++cr)
+            gv[cr] = reinterpret_cast<const int*>(sm.grecv)[min(cr, cluster_size - 1) * 16 + (lane & 15)];
+#pragma unroll
+          for (int cr = 0; cr < kMaxC; ++cr) ge += cr < cluster_size ? gv[cr] : 0;
+        }
         float b2[R * R];
 #pragma unroll
         for (int j = 0; j < R; ++j)
@@ -484,12 +490,18 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
         float f[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         if (tid < npr) {
           long long s[4] = {0, 0, 0, 0};
+          {
+            longlong2 q0[kMaxC], q1[kMaxC];
 #pragma unroll
-          for (int cr = 0; cr < kMaxC; ++cr) {
-            const bool on = cr < cluster_size;
-            const int slot = on ? ((cr << npr_log) + tid) * 2 : 0;
-            const longlong2 q0 = sm.srecv[slot], q1 = sm.srecv[slot + 1];
-            s[0] += on ? q0.x : 0, s[1] += on ? q0.y : 0, s[2] += on ? q1.x : 0, s[3] += on ? q1.y : 0;
+            for (int cr = 0; cr < kMaxC; ++cr) {
+              const int slot = ((min(cr, cluster_size - 1) << npr_log) + tid) * 2;
+              q0[cr] = sm.srecv[slot], q1[cr] = sm.srecv[slot + 1];
+            }
+#pragma unroll
+            for (int cr = 0; cr < kMaxC; ++cr) {
+              const bool on = cr < cluster_size;
+              s[0] += on ? q0[cr].x : 0, s[1] += on ? q0[cr].y : 0, s[2] += on ? q1[cr].x : 0, s[3] += on ? q1[cr].y : 0;
+            }
           }
           TC_TRACE(12)
           const int n = crank * npr + tid;

@@ -388,8 +388,119 @@ eig_topr_kernel(const double* __restrict__ Gin, int Nrt, int R, double* __restri
 // global memory and read back, coalesced, for the back-transformation.  Phases 2-5 as in the generic
 // kernel, with the multisection split across the two warps.
 // ---------------------------------------------------------------------------------------------------
+// N = 64 specialisations used by eig64_topr_kernel: same arithmetic as sturm_count / tridiag_inverse_iteration, but
+// fully unrolled so that the loads of d, e^2 and the LU factors run ahead of the recurrences (the generic versions
+// pay a shared-memory round trip per dependent step), and the iterate z lives in registers.
+__device__ __forceinline__ int sturm_count64(const double* __restrict__ d, const double* __restrict__ e2, double x,
+                                             double pivmin) {
+  double pm = 1.0;  // p_{i-1}
+  double p = d[0] - x;
+  if (fabs(p) < pivmin) p = -pivmin;
+  int cnt = p < 0.0;
+#pragma unroll 8
+  for (int i = 1; i < 64; ++i) {
+    double pn = fma(d[i] - x, p, -e2[i - 1] * pm);
+    pn = fabs(pn) < pivmin * fabs(p) ? -pivmin * p : pn;
+    cnt += (pn < 0.0) != (p < 0.0);
+    const double a = fabs(pn);
+    const double sc = a > 1e100 ? 1e-100 : (a < 1e-100 ? 1e100 : 1.0);
+    pm = p * sc, p = pn * sc;
+  }
+  return cnt;
+}
+
+__device__ __forceinline__ void tridiag_inverse_iteration64(const double* __restrict__ d, const double* __restrict__ e,
+                                                            double lam, double tnorm, double* __restrict__ zout,
+                                                            double* __restrict__ lu, int seed) {
+  constexpr int N = 64;
+  double* dl = lu;
+  double* dd = lu + N;
+  double* du = lu + 2 * N;
+  double* du2 = lu + 3 * N;
+  double* piv = lu + 4 * N;
+  const double tol = fmax(tnorm, 1e-300) * 2.3e-16;
+  // pivoted LU (dgttrf): the running diagonal / super-diagonal entries are carried in registers
+  double ddi = d[0] - lam, dui = e[0];
+#pragma unroll 4
+  for (int i = 0; i < N - 1; ++i) {
+    const double dli = e[i];
+    double dd_next = d[i + 1] - lam;
+    double du_next = (i + 1 < N - 1) ? e[i + 1] : 0.0;
+    if (fabs(ddi) >= fabs(dli)) {
+      if (fabs(ddi) < tol) ddi = (ddi < 0.0) ? -tol : tol;
+      const double rc = 1.0 / ddi;
+      const double f = dli * rc;
+      dl[i] = f, dd[i] = rc, du[i] = dui, du2[i] = 0.0, piv[i] = 0.0;
+      dd_next -= f * dui;
+    } else {
+      const double rc = 1.0 / dli;
+      const double f = ddi * rc;
+      dd[i] = rc, dl[i] = f, du[i] = dd_next, piv[i] = 1.0;
+      dd_next = dui - f * dd_next;
+      if (i < N - 2) {
+        du2[i] = du_next;
+        du_next = -f * du_next;
+      } else {
+        du2[i] = 0.0;
+      }
+    }
+    ddi = dd_next, dui = du_next;
+  }
+  if (fabs(ddi) < tol) ddi = (ddi < 0.0) ? -tol : tol;
+  dd[N - 1] = 1.0 / ddi, du[N - 1] = 0.0, du2[N - 1] = 0.0, piv[N - 1] = 0.0, dl[N - 1] = 0.0;
+
+  // the iterate stays in shared memory (z = zout), but every recurrence carries its running values in registers, so
+  // all loads are independent of the dependent chain and run ahead of it
+  double* z = zout;
+  unsigned s = 12345u + 7919u * (unsigned)seed;
+#pragma unroll 8
+  for (int i = 0; i < N; ++i) {  // deterministic start vector with no special structure
+    s = s * 1664525u + 1013904223u;
+    z[i] = 0.5 + (double)(s >> 8) * (1.0 / 16777216.0);
+  }
+#pragma unroll 1
+  for (int it = 0; it < 3; ++it) {
+    double zc = z[0];
+#pragma unroll 8
+    for (int i = 0; i < N - 1; ++i) {  // L^-1 with the row interchanges
+      const double zn = z[i + 1], li = dl[i];
+      const bool swapped = piv[i] != 0.0;
+      const double zi = swapped ? zn : zc;
+      const double zo = swapped ? zc : zn;
+      z[i] = zi;
+      zc = zo - li * zi;
+    }
+    double zp2 = zc * dd[N - 1];
+    double zp1 = (z[N - 2] - du[N - 2] * zp2) * dd[N - 2];
+    z[N - 1] = zp2, z[N - 2] = zp1;
+    double mx = fmax(fabs(zp1), fabs(zp2));
+#pragma unroll 8
+    for (int i = N - 3; i >= 0; --i) {  // U^-1
+      const double zi = (z[i] - du[i] * zp1 - du2[i] * zp2) * dd[i];
+      z[i] = zi;
+      mx = fmax(mx, fabs(zi));
+      zp2 = zp1, zp1 = zi;
+    }
+    if (!(mx > 0.0) || !(mx < 1e300)) {  // breakdown guard: restart from a basis vector
+#pragma unroll 1
+      for (int i = 0; i < N; ++i) z[i] = (i == seed % N) ? 1.0 : 0.0;
+      mx = 1.0;
+    }
+    double inv = 1.0 / mx, nrm = 0.0;
+#pragma unroll 8
+    for (int i = 0; i < N; ++i) {
+      const double t = z[i] * inv;
+      z[i] = t;
+      nrm = fma(t, t, nrm);
+    }
+    nrm = 1.0 / sqrt(nrm);
+#pragma unroll 8
+    for (int i = 0; i < N; ++i) z[i] *= nrm;
+  }
+}
+
 struct Eig64Smem {
-  double xs[64], vv[64], w[64], d[64], e[64], tau[64];
+  double xs[64], vv[64], w[64], d[64], e[64], e2[64], tau[64];
   double red[4];
   double lam[4];
   double z[4 * 64];
@@ -405,7 +516,14 @@ __device__ __forceinline__ double block64_sum(double v, double* red, int tid) { 
   return s;
 }
 
-__global__ void __launch_bounds__(64)
+#ifdef LRFB_EIG_TRACE
+__device__ long long g_eig_trace[8];  // probe build only (tools/probes/eig_trace.cu)
+#define EIG_TRACE(pt) if (blockIdx.x == 0 && threadIdx.x == 0) g_eig_trace[pt] = clock64();
+#else
+#define EIG_TRACE(pt)
+#endif
+
+__global__ void __launch_bounds__(64, 6)
 eig64_topr_kernel(double* __restrict__ G, int R, double* __restrict__ evec_out, double* __restrict__ sigma_out,
                   const int* __restrict__ sign_flip, int M_rows, float* __restrict__ v0_out,
                   float* __restrict__ s0_out) {
@@ -417,19 +535,29 @@ eig64_topr_kernel(double* __restrict__ G, int R, double* __restrict__ evec_out, 
 #pragma unroll
   for (int j = 0; j < N; ++j) a[j] = g[j * N + tid];
 
+  EIG_TRACE(0)
   // ---- 1. tridiagonalisation ----
 #pragma unroll 1
   for (int k = 0; k < N - 2; ++k) {
     if (warp == (k >> 5)) {
       if (tid == k) {
+        // column k = row k (symmetric): x and the diagonal; its owner also forms |x_{k+2..}|^2 (no block reduction)
+        double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
 #pragma unroll
-        for (int j = 0; j < N; ++j) sm.xs[j] = a[j];  // column k = row k (symmetric): x and the diagonal
+        for (int j = 0; j < N; j += 4) {
+          sm.xs[j] = a[j], sm.xs[j + 1] = a[j + 1], sm.xs[j + 2] = a[j + 2], sm.xs[j + 3] = a[j + 3];
+          q0 = fma(j + 0 >= k + 2 ? a[j + 0] : 0.0, a[j + 0], q0);
+          q1 = fma(j + 1 >= k + 2 ? a[j + 1] : 0.0, a[j + 1], q1);
+          q2 = fma(j + 2 >= k + 2 ? a[j + 2] : 0.0, a[j + 2], q2);
+          q3 = fma(j + 3 >= k + 2 ? a[j + 3] : 0.0, a[j + 3], q3);
+        }
+        sm.red[2] = (q0 + q1) + (q2 + q3);
       }
     }
     __syncthreads();
     const double alpha0 = sm.xs[k + 1];
     const double xc = sm.xs[tid];
-    const double xn2 = block64_sum(tid >= k + 2 ? xc * xc : 0.0, sm.red, tid);
+    const double xn2 = sm.red[2];
     double beta, tk, scal;
     if (xn2 == 0.0) {
       beta = alpha0, tk = 0.0, scal = 0.0;
@@ -469,7 +597,10 @@ eig64_topr_kernel(double* __restrict__ G, int R, double* __restrict__ evec_out, 
   if (tid == N - 2) sm.d[N - 2] = a[N - 2], sm.e[N - 2] = a[N - 1], sm.tau[N - 2] = 0.0;
   if (tid == N - 1) sm.d[N - 1] = a[N - 1], sm.e[N - 1] = 0.0, sm.tau[N - 1] = 0.0;
   __syncthreads();
+  sm.e2[tid] = sm.e[tid] * sm.e[tid];
+  __syncthreads();
 
+  EIG_TRACE(1)
   // ---- 2. R largest eigenvalues: each warp multisects its share of the eigenvalues ----
   const double* d = sm.d;
   const double* e = sm.e;
@@ -503,7 +634,7 @@ eig64_topr_kernel(double* __restrict__ G, int R, double* __restrict__ evec_out, 
     for (int round = 0; round < rounds; ++round) {
       const double step = (hi - lo) / (double)(ppe + 1);
       const double x = lo + step * (double)(pr + 1);
-      const int cnt = active ? sturm_count(d, e, N, x, pivmin) : 0;
+      const int cnt = active ? sturm_count64(d, sm.e2, x, pivmin) : 0;
       const unsigned ballot = __ballot_sync(0xffffffffu, active && cnt > idx);
       const unsigned bits = (ppe == 32) ? ballot : ((ballot >> (grp * ppe)) & ((1u << ppe) - 1u));
       const int f = bits ? (__ffs((int)bits) - 1) : ppe;
@@ -515,48 +646,42 @@ eig64_topr_kernel(double* __restrict__ G, int R, double* __restrict__ evec_out, 
   }
   __syncthreads();
 
-  // ---- 3. eigenvectors of the tridiagonal (one thread each), MGS by thread 0 ----
-  if (tid < R) tridiag_inverse_iteration(d, e, N, sm.lam[tid], tnorm, sm.z + tid * N, sm.lu + tid * 5 * N, tid);
+  EIG_TRACE(2)
+  // ---- 3. eigenvectors of the tridiagonal (one thread each, iterate in registers); cooperative MGS ----
+  if (tid < R) tridiag_inverse_iteration64(d, e, sm.lam[tid], tnorm, sm.z + tid * N, sm.lu + tid * 5 * N, tid);
   __syncthreads();
-  if (tid == 0) {
-    for (int r = 0; r < R; ++r) {
-      double* zr = sm.z + r * N;
-      for (int q = 0; q < r; ++q) {
-        const double* zq = sm.z + q * N;
-        double dot = 0.0;
-#pragma unroll 1
-        for (int i = 0; i < N; ++i) dot = fma(zr[i], zq[i], dot);
-#pragma unroll 1
-        for (int i = 0; i < N; ++i) zr[i] = fma(-dot, zq[i], zr[i]);
-      }
-      double nrm = 0.0;
-#pragma unroll 1
-      for (int i = 0; i < N; ++i) nrm = fma(zr[i], zr[i], nrm);
-      if (nrm < 1e-20) {  // degenerate input: fall back to a basis vector
-#pragma unroll 1
-        for (int i = 0; i < N; ++i) zr[i] = (i == r) ? 1.0 : 0.0;
-        for (int q = 0; q < r; ++q) {
-          const double* zq = sm.z + q * N;
-          const double dot = zq[r];
-#pragma unroll 1
-          for (int i = 0; i < N; ++i) zr[i] = fma(-dot, zq[i], zr[i]);
-        }
-        nrm = 0.0;
-#pragma unroll 1
-        for (int i = 0; i < N; ++i) nrm = fma(zr[i], zr[i], nrm);
-        if (nrm < 1e-20) nrm = 1.0;
-      }
-      nrm = 1.0 / sqrt(nrm);
-#pragma unroll 1
-      for (int i = 0; i < N; ++i) zr[i] *= nrm;
-    }
-  }
-  __syncthreads();
-
-  // ---- 4. back-transform: thread c holds element c of each vector and column c of the reflectors ----
-  double zc[4];
+  EIG_TRACE(3)
+  double zc[4];  // thread c holds element c of each vector
 #pragma unroll
   for (int q = 0; q < 4; ++q) zc[q] = q < R ? sm.z[q * N + tid] : 0.0;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    if (r < R) {  // uniform
+#pragma unroll
+      for (int q = 0; q < r; ++q) {
+        const double dot = block64_sum(zc[r] * zc[q], sm.red, tid);
+        zc[r] = fma(-dot, zc[q], zc[r]);
+      }
+      double nrm = block64_sum(zc[r] * zc[r], sm.red, tid);
+      if (nrm < 1e-20) {  // degenerate input: fall back to a basis vector (uniform branch)
+        zc[r] = (tid == r) ? 1.0 : 0.0;
+#pragma unroll
+        for (int q = 0; q < r; ++q) {
+          if (tid == r) sm.xs[q] = zc[q];  // element r of vector q
+          __syncthreads();
+          const double dot = sm.xs[q];
+          __syncthreads();
+          zc[r] = fma(-dot, zc[q], zc[r]);
+        }
+        nrm = block64_sum(zc[r] * zc[r], sm.red, tid);
+        if (nrm < 1e-20) nrm = 1.0;
+      }
+      zc[r] *= 1.0 / sqrt(nrm);
+    }
+  }
+
+  EIG_TRACE(4)
+  // ---- 4. back-transform: thread c holds element c of each vector and column c of the reflectors ----
 #pragma unroll
   for (int k = 0; k < N - 2; ++k) a[k] = g[k * N + tid];  // reflector k, element `tid` (written by this thread)
 #pragma unroll
@@ -576,6 +701,7 @@ eig64_topr_kernel(double* __restrict__ G, int R, double* __restrict__ evec_out, 
     __syncthreads();
   }
 
+  EIG_TRACE(5)
   // ---- 5. sign convention (sum(v) <= 0, see eig_topr_kernel) and output ----
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
@@ -591,6 +717,7 @@ eig64_topr_kernel(double* __restrict__ G, int R, double* __restrict__ evec_out, 
     v0_out[((size_t)mat * N + tid) * R + r] = kept ? __fmul_rn((float)(sg * zc[r]), rs) : 0.0f;
     if (tid == 0) sigma_out[(size_t)mat * R + r] = sig, s0_out[(size_t)mat * R + r] = s32;
   }
+  EIG_TRACE(6)
 }
 
 }  // namespace lrfb
