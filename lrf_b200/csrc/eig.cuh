@@ -393,18 +393,23 @@ eig_topr_kernel(const double* __restrict__ Gin, int Nrt, int R, double* __restri
 // pay a shared-memory round trip per dependent step), and the iterate z lives in registers.
 __device__ __forceinline__ int sturm_count64(const double* __restrict__ d, const double* __restrict__ e2, double x,
                                              double pivmin) {
+  // Scaled minors as in sturm_count, but the scale factor of step i is chosen from the magnitude seen at step i-1
+  // (a minor grows by at most |d - x| + e^2 < 1e20 per step, the thresholds leave 200 decades) and is a power of two
+  // (exact), so it is off the dependent chain fma -> mul -> fma and never changes a sign.
   double pm = 1.0;  // p_{i-1}
   double p = d[0] - x;
   if (fabs(p) < pivmin) p = -pivmin;
   int cnt = p < 0.0;
+  double sc = 1.0;
 #pragma unroll 8
   for (int i = 1; i < 64; ++i) {
-    double pn = fma(d[i] - x, p, -e2[i - 1] * pm);
-    pn = fabs(pn) < pivmin * fabs(p) ? -pivmin * p : pn;
-    cnt += (pn < 0.0) != (p < 0.0);
-    const double a = fabs(pn);
-    const double sc = a > 1e100 ? 1e-100 : (a < 1e-100 ? 1e100 : 1.0);
-    pm = p * sc, p = pn * sc;
+    const double ps = p * sc, pms = pm * sc;  // rescaled pair (p_{i-1}, p_{i-2})
+    double pn = fma(d[i] - x, ps, -e2[i - 1] * pms);
+    pn = fabs(pn) < pivmin * fabs(ps) ? -pivmin * ps : pn;
+    cnt += (pn < 0.0) != (ps < 0.0);
+    const double a = fabs(ps);
+    sc = a > 0x1p+332 ? 0x1p-332 : (a < 0x1p-332 ? 0x1p+332 : 1.0);  // applied at the next step
+    pm = ps, p = pn;
   }
   return cnt;
 }
@@ -501,11 +506,20 @@ __device__ __forceinline__ void tridiag_inverse_iteration64(const double* __rest
 
 struct Eig64Smem {
   double xs[64], vv[64], w[64], d[64], e[64], e2[64], tau[64];
-  double red[4];
+  double red[8];
   double lam[4];
   double z[4 * 64];
   double lu[4 * 5 * 64];
 };
+
+// one-barrier variant: the caller alternates `slot` (0/1) between consecutive uses, so a slow reader of one use never
+// meets the writes of the next
+__device__ __forceinline__ double block64_sum_alt(double v, double* red, int tid, int slot) {
+  v = warp_sum(v);
+  if ((tid & 31) == 0) red[slot * 2 + (tid >> 5)] = v;
+  __syncthreads();
+  return red[slot * 2] + red[slot * 2 + 1];
+}
 
 __device__ __forceinline__ double block64_sum(double v, double* red, int tid) {  // 2 warps; every thread gets the sum
   v = warp_sum(v);
@@ -551,13 +565,13 @@ eig64_topr_kernel(double* __restrict__ G, int R, double* __restrict__ evec_out, 
           q2 = fma(j + 2 >= k + 2 ? a[j + 2] : 0.0, a[j + 2], q2);
           q3 = fma(j + 3 >= k + 2 ? a[j + 3] : 0.0, a[j + 3], q3);
         }
-        sm.red[2] = (q0 + q1) + (q2 + q3);
+        sm.red[4] = (q0 + q1) + (q2 + q3);
       }
     }
     __syncthreads();
     const double alpha0 = sm.xs[k + 1];
     const double xc = sm.xs[tid];
-    const double xn2 = sm.red[2];
+    const double xn2 = sm.red[4];
     double beta, tk, scal;
     if (xn2 == 0.0) {
       beta = alpha0, tk = 0.0, scal = 0.0;
@@ -582,7 +596,7 @@ eig64_topr_kernel(double* __restrict__ G, int R, double* __restrict__ evec_out, 
         s3 = fma(a[j + 3], sm.vv[j + 3], s3);
       }
       const double pc = tid > k ? tk * ((s0 + s1) + (s2 + s3)) : 0.0;
-      const double kk = 0.5 * tk * block64_sum(pc * vc, sm.red, tid);
+      const double kk = 0.5 * tk * block64_sum_alt(pc * vc, sm.red, tid, k & 1);
       const double wc = tid > k ? fma(-kk, vc, pc) : 0.0;
       sm.w[tid] = wc;
       __syncthreads();
@@ -592,8 +606,9 @@ eig64_topr_kernel(double* __restrict__ G, int R, double* __restrict__ evec_out, 
         a[j] = fma(-sm.w[j], vc, t);
       }
     }
-    __syncthreads();
+    // no barrier here: the next step's first writes (xs, red[4]) were last read before this step's second barrier
   }
+  __syncthreads();
   if (tid == N - 2) sm.d[N - 2] = a[N - 2], sm.e[N - 2] = a[N - 1], sm.tau[N - 2] = 0.0;
   if (tid == N - 1) sm.d[N - 1] = a[N - 1], sm.e[N - 1] = 0.0, sm.tau[N - 1] = 0.0;
   __syncthreads();
