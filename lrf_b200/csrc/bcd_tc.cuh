@@ -206,17 +206,9 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
     ++mats_seen;
 #endif
 
-    // ---- load this CTA's slice of X once (swizzled f32) and V ----
+    // ---- V first (the cluster barrier above separates it from the previous matrix), then this CTA's slice of X
+    //      (swizzled f32, cp.async); the 64-step chains of V^T V run while the rows are in flight ----
     TC_TRACE_S(0)
-    __syncthreads();
-    TC_TRACE_S(1)
-    for (int c = tid; c < kTcRows * (N / 4); c += NT) {
-      const int row = c >> 4, ch = c & 15;
-      float* dst = &sm.x[row * N + ((ch ^ (row & 7)) << 2)];
-      if (row < rows_here) cp_async16(dst, X + (size_t)(row0 + row) * N + ch * 4);
-      else dst[0] = dst[1] = dst[2] = dst[3] = 0.0f;
-    }
-    cp_async_commit();
     for (int i = tid; i < N * R; i += NT) sm.v[i] = V[i];
     if (tid < R) {
       float inv = 0.0f;
@@ -226,12 +218,21 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
       }
       sm.s0inv[tid] = inv;
     }
+    __syncthreads();
+    TC_TRACE_S(1)
+    for (int c = tid; c < kTcRows * (N / 4); c += NT) {
+      const int row = c >> 4, ch = c & 15;
+      float* dst = &sm.x[row * N + ((ch ^ (row & 7)) << 2)];
+      if (row < rows_here) cp_async16(dst, X + (size_t)(row0 + row) * N + ch * 4);
+      else dst[0] = dst[1] = dst[2] = dst[3] = 0.0f;
+    }
+    cp_async_commit();
     const float* Uinit = P.U + (size_t)mat * M * R + (size_t)row0 * R;
     TC_TRACE_S(2)
+    gram_small<N, R>(sm.v, sm.b, tid);
+    TC_TRACE_S(3)
     cp_async_wait<0>();
     __syncthreads();
-    TC_TRACE_S(3)
-    gram_small<N, R>(sm.v, sm.b, tid);
     TC_TRACE_S(4)
 
     // ---- Q8.24 byte planes of X into tensor memory (A operand of the V-phase MMAs) ----
@@ -268,7 +269,7 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
     TC_TRACE_S(5)
     // the first kReg A-phase rows of this thread stay in registers for all sweeps
     // the 2-CTAs-per-SM shape must stay within 128 registers; 256 threads x 3 rows have room for two register rows
-    constexpr int kReg = (ROWS <= 384) ? 0 : (NT == 256 ? 2 : (R == 4 ? 1 : 0));
+    constexpr int kReg = (ROWS <= 384) ? 0 : (NT == 256 ? 2 : 1);
     constexpr int kRegN = kReg ? N : 1;
     float xr[kReg ? kReg : 1][kRegN];
 #pragma unroll

@@ -712,6 +712,10 @@ LRFB_EXPORT int32_t lrfb_qmf_encode(const lrfb_qmf_config* cfg, int32_t batch, c
       if ((rc = run_plane(2, 1, side->stream2))) return rc;
       cudaEventRecord(side->init2, side->stream2);
       if (timeline) cudaEventRecord(ev[3], side->stream2);
+      // the chroma sweeps become runnable together with the luma sweeps, not before: the (higher-priority) luma clusters
+      // are placed first and the chroma clusters take the SMs they leave; later chroma clusters start as SMs free up
+      cudaEventRecord(side->join, st);
+      cudaStreamWaitEvent(side->stream, side->join, 0);
       if ((rc = run_plane(0, 2, st))) return rc;
       if (timeline) cudaEventRecord(ev[4], st);
       if ((rc = run_plane(1, 2, side->stream))) return rc;

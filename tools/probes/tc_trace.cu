@@ -7,7 +7,8 @@
 #include <random>
 using namespace lrfb;
 int main(int argc, char** argv) {
-  const int B = 240, M = 6144, N = 64, R = 4;
+  const bool chroma = argc > 1 && atoi(argv[1]) == 2;  // 2: chroma shape (1536 rows, R = 2, clusters of 2)
+  const int B = chroma ? 592 : 240, M = chroma ? 1536 : 6144, N = 64, R = chroma ? 2 : 4;
   std::vector<float> hx((size_t)B * M * N), hv((size_t)B * N * R), hu((size_t)B * M * R);
   std::mt19937 rng(1);
   std::uniform_real_distribution<float> d(0.0f, 255.0f), dv(-1.0f, 1.0f);
@@ -26,9 +27,9 @@ int main(int argc, char** argv) {
   cudaMalloc(&counter, 4);
   b.work_counter = counter;
   const bool small = argc > 1 && atoi(argv[1]) == 1;  // 1: 384 rows x 192 threads, clusters of 16, 2 CTAs per SM
-  auto kern = small ? bcd_tc_kernel<4, 384, 192> : bcd_tc_kernel<4, 768, 384>;
-  const size_t smem = small ? sizeof(TcSmem<4, 384, 192>) : sizeof(TcSmem<4, 768, 384>);
-  const int csize = small ? 16 : 8, nt = small ? 192 : 384, rows = small ? 384 : 768;
+  auto kern = chroma ? bcd_tc_kernel<2, 768, 384> : small ? bcd_tc_kernel<4, 384, 192> : bcd_tc_kernel<4, 768, 384>;
+  const size_t smem = chroma ? sizeof(TcSmem<2, 768, 384>) : small ? sizeof(TcSmem<4, 384, 192>) : sizeof(TcSmem<4, 768, 384>);
+  const int csize = chroma ? 2 : small ? 16 : 8, nt = small ? 192 : 384, rows = small ? 384 : 768;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
@@ -36,7 +37,7 @@ int main(int argc, char** argv) {
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = csize, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-  cfg.blockDim = dim3(nt), cfg.dynamicSmemBytes = smem, cfg.attrs = attr, cfg.numAttrs = 1, cfg.gridDim = dim3(small ? 224 : 120);
+  cfg.blockDim = dim3(nt), cfg.dynamicSmemBytes = smem, cfg.attrs = attr, cfg.numAttrs = 1, cfg.gridDim = dim3(chroma ? 148 : small ? 224 : 120);
   for (int rep = 0; rep < 2; ++rep) {
     cudaMemset(counter, 0, 4);
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, b, csize, rows);
@@ -56,7 +57,7 @@ int main(int argc, char** argv) {
     printf("\n");
   }
   const long long* t = h + 14 * 12;
-  printf("second matrix of CTA 0: barrier %lld | loads issued %lld | X landed %lld | gram_small %lld | byte planes in TMEM %lld | register row + barrier %lld | 10 sweeps %lld\n",
+  printf("second matrix of CTA 0: V + barrier %lld | loads issued %lld | gram_small %lld | X landed %lld | byte planes in TMEM %lld | register row + barrier %lld | 10 sweeps %lld\n",
          t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] - t[4], t[6] - t[5], t[7] - t[6]);
   return 0;
 }
