@@ -354,7 +354,7 @@ def main():
             "host_pack": {"images": n_s, "seconds": pack_s, "threads": os.cpu_count(),
                           "mpixel_per_s": n_s * H * W / 1e6 / pack_s},
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # N = 1 only: the other ranks must not wait on host work
             cores = os.cpu_count() or 1
             v, dt = cpu_reference_mpix(args.cpu_sample, cores)
             line["cpu_baseline"] = {"value": v, "unit": "Mpixel/s", "cores": cores, "kind": "port",
