@@ -104,7 +104,15 @@ __device__ __forceinline__ float ycc_from(float r, float g, float b, int c) {
   acc = __fmaf_rn(t2, b, acc);
   return __fadd_rn(off, acc);
 }
-__device__ __forceinline__ float byte_of(unsigned w, int k) { return (float)((w >> (8 * k)) & 0xffu); }
+// byte k of w as a float: PRMT drops the byte into the mantissa of 2^23, one exact subtraction removes the 2^23
+// (two full-rate instructions instead of shift + mask + quarter-rate I2F)
+__device__ __forceinline__ float byte_of(unsigned w, int k) {
+#ifdef LRFB_SIM
+  return (float)((w >> (8 * k)) & 0xffu);
+#else
+  return __fsub_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u + k)), 8388608.0f);
+#endif
+}
 }  // namespace
 
 __global__ void __launch_bounds__(256)
@@ -242,9 +250,9 @@ frontend8_fused_kernel(const unsigned char* __restrict__ images, float* __restri
         *reinterpret_cast<float4*>(d + 4) = make_float4(lum[4], lum[5], lum[6], lum[7]);
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        sb[j] = __fdiv_rn(__fdiv_rn(sb[j], 2.0f), 2.0f);
-        sr[j] = __fdiv_rn(__fdiv_rn(sr[j], 2.0f), 2.0f);
+      for (int j = 0; j < 4; ++j) {  // (s / 2) / 2: scaling by a power of two is exact, so two multiplies give the same bits
+        sb[j] = __fmul_rn(__fmul_rn(sb[j], 0.5f), 0.5f);
+        sr[j] = __fmul_rn(__fmul_rn(sr[j], 0.5f), 0.5f);
       }
       const int co = (wp >> 1) * kTilePatchStride + cy * 8 + (wp & 1) * 4;
       *reinterpret_cast<float4*>(&s_cb[co]) = make_float4(sb[0], sb[1], sb[2], sb[3]);
@@ -253,17 +261,30 @@ frontend8_fused_kernel(const unsigned char* __restrict__ images, float* __restri
     __syncthreads();
     // write-out: 2 runs of n_lp luma patches, 1 run of n_cp patches per chroma plane, all contiguous in X
     float* oy = xy + (size_t)im * gl.rows * 64;
-    for (int i = tid; i < 2 * n_lp * 16; i += 256) {
-      const int pr = i / (n_lp * 16), rem = i - pr * n_lp * 16, patch = rem >> 4, q = rem & 15;
-      const float4 v = *reinterpret_cast<const float4*>(&s_lum[(pr * 32 + patch) * kTilePatchStride + q * 4]);
-      *reinterpret_cast<float4*>(oy + ((size_t)((y0 >> 3) + pr) * nbl + wp0 + patch) * 64 + q * 4) = v;
-    }
     float* ocb = xcb + (size_t)im * gc.rows * 64;
     float* ocr = xcr + (size_t)im * gc.rows * 64;
-    for (int i = tid; i < 2 * n_cp * 16; i += 256) {
-      const int pl = i / (n_cp * 16), rem = i - pl * n_cp * 16, patch = rem >> 4, q = rem & 15;
-      const float4 v = *reinterpret_cast<const float4*>(&(pl ? s_cr : s_cb)[patch * kTilePatchStride + q * 4]);
-      *reinterpret_cast<float4*>((pl ? ocr : ocb) + ((size_t)(y0 >> 4) * nbc + (wp0 >> 1) + patch) * 64 + q * 4) = v;
+    if (n_lp == 32) {  // full tile (every tile when W % 256 == 0): index math in shifts, 4 + 2 stores per thread
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int i = tid + t * 256, pr = i >> 9, patch = (i >> 4) & 31, q = i & 15;
+        const float4 v = *reinterpret_cast<const float4*>(&s_lum[(pr * 32 + patch) * kTilePatchStride + q * 4]);
+        *reinterpret_cast<float4*>(oy + ((size_t)((y0 >> 3) + pr) * nbl + wp0 + patch) * 64 + q * 4) = v;
+      }
+      const int patch = tid >> 4, q = tid & 15;
+      const size_t co = ((size_t)(y0 >> 4) * nbc + (wp0 >> 1) + patch) * 64 + q * 4;
+      *reinterpret_cast<float4*>(ocb + co) = *reinterpret_cast<const float4*>(&s_cb[patch * kTilePatchStride + q * 4]);
+      *reinterpret_cast<float4*>(ocr + co) = *reinterpret_cast<const float4*>(&s_cr[patch * kTilePatchStride + q * 4]);
+    } else {
+      for (int i = tid; i < 2 * n_lp * 16; i += 256) {
+        const int pr = i / (n_lp * 16), rem = i - pr * n_lp * 16, patch = rem >> 4, q = rem & 15;
+        const float4 v = *reinterpret_cast<const float4*>(&s_lum[(pr * 32 + patch) * kTilePatchStride + q * 4]);
+        *reinterpret_cast<float4*>(oy + ((size_t)((y0 >> 3) + pr) * nbl + wp0 + patch) * 64 + q * 4) = v;
+      }
+      for (int i = tid; i < 2 * n_cp * 16; i += 256) {
+        const int pl = i / (n_cp * 16), rem = i - pl * n_cp * 16, patch = rem >> 4, q = rem & 15;
+        const float4 v = *reinterpret_cast<const float4*>(&(pl ? s_cr : s_cb)[patch * kTilePatchStride + q * 4]);
+        *reinterpret_cast<float4*>((pl ? ocr : ocb) + ((size_t)(y0 >> 4) * nbc + (wp0 >> 1) + patch) * 64 + q * 4) = v;
+      }
     }
   }
 }
