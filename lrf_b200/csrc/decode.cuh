@@ -162,6 +162,101 @@ qmf_decode8_kernel(const int8_t* __restrict__ factors, unsigned char* __restrict
   }
 }
 
+#ifndef LRFB_SIM
+// ---------------------------------------------------------------------------------------------------
+// Faster path for the unpadded geometry (H, W multiples of 16, chroma exactly half size) and ranks <= 4: one thread
+// reconstructs an 8-pixel x 2-row strip.  u @ v.T on small integers is exact in any arithmetic (|sum| <= 4*128*128),
+// so it is done as int8 dot products: the 4 ranks of U in one word, the V bytes of the 4 ranks transposed into one
+// word per pixel (PRMT), one DP4A per pixel instead of 4 x (convert, multiply, add).  The two rows share the luma U
+// word and the whole chroma reconstruction (nearest up-sampling).  Colour transform and u8 conversion as above.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void transpose4x4_bytes(unsigned a, unsigned b, unsigned c, unsigned d, unsigned (&w)[4]) {
+  const unsigned t0 = __byte_perm(a, b, 0x5140), t1 = __byte_perm(a, b, 0x7362);
+  const unsigned u0 = __byte_perm(c, d, 0x5140), u1 = __byte_perm(c, d, 0x7362);
+  w[0] = __byte_perm(t0, u0, 0x5410), w[1] = __byte_perm(t0, u0, 0x7632);
+  w[2] = __byte_perm(t1, u1, 0x5410), w[3] = __byte_perm(t1, u1, 0x7632);
+}
+
+__global__ void __launch_bounds__(256)
+qmf_decode8x2_kernel(const int8_t* __restrict__ factors, unsigned char* __restrict__ out, DecodeParams P) {
+  const float t[3][3] = {{1.0f, 0.0f, 1.40200f}, {1.0f, -0.344136f, -0.714136f}, {1.0f, 1.77200f, 0.0f}};
+  const size_t hw = (size_t)P.H * P.W;
+  const int segs = P.W / 8;
+  const long long items = (long long)(P.H / 2) * segs;
+  const PlaneGeom gy = P.g[0], gc = P.g[1];
+  for (int im = blockIdx.y; im < P.n_img; im += gridDim.y) {
+    const int8_t* rec = factors + (size_t)im * P.record_bytes;
+    unsigned char* o = out + (size_t)im * 3 * hw;
+    for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items;
+         it += (long long)gridDim.x * blockDim.x) {
+      const int cy = (int)(it / segs), sg = (int)(it - (long long)cy * segs);
+      // ---- chroma: 4 columns 4*sg .. 4*sg+3 of chroma row cy, both planes ----
+      int pc[2][4];
+      {
+        const int cx0 = 4 * sg, m = (cy >> 3) * gc.nbw + (cx0 >> 3), col = (cy & 7) * 8 + (cx0 & 7);
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl) {
+          const int8_t* u = rec + P.u_off[1 + pl];
+          const int8_t* v = rec + P.v_off[1 + pl];
+          unsigned uw = 0, vr[4] = {0, 0, 0, 0}, w[4];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            if (r < P.rank[1 + pl]) {
+              uw |= (unsigned)(unsigned char)u[(size_t)r * gc.rows + m] << (8 * r);
+              vr[r] = *reinterpret_cast<const unsigned*>(v + (size_t)r * 64 + col);
+            }
+          }
+          transpose4x4_bytes(vr[0], vr[1], vr[2], vr[3], w);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) pc[pl][j] = __dp4a((int)w[j], (int)uw, 0);
+        }
+      }
+      float cb[4], cr[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) cb[j] = __fadd_rn((float)pc[0][j], -128.0f), cr[j] = __fadd_rn((float)pc[1][j], -128.0f);
+      // ---- luma: rows 2cy and 2cy+1 lie in the same patch row, so they share the U word ----
+      const int y0 = 2 * cy, m = (y0 >> 3) * gy.nbw + sg;
+      const int8_t* u = rec + P.u_off[0];
+      const int8_t* v = rec + P.v_off[0];
+      unsigned uw = 0;
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        if (r < P.rank[0]) uw |= (unsigned)(unsigned char)u[(size_t)r * gy.rows + m] << (8 * r);
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy) {
+        const int y = y0 + dy, col = (y & 7) * 8;
+        uint2 vr[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          vr[r] = make_uint2(0u, 0u);
+          if (r < P.rank[0]) vr[r] = *reinterpret_cast<const uint2*>(v + (size_t)r * 64 + col);
+        }
+        unsigned wl[4], wh[4];
+        transpose4x4_bytes(vr[0].x, vr[1].x, vr[2].x, vr[3].x, wl);
+        transpose4x4_bytes(vr[0].y, vr[1].y, vr[2].y, vr[3].y, wh);
+        unsigned lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float yv = (float)__dp4a((int)(j < 4 ? wl[j & 3] : wh[j & 3]), (int)uw, 0);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            float acc = __fmul_rn(t[c][0], yv);
+            acc = __fmaf_rn(t[c][1], cb[j >> 1], acc);
+            acc = __fmaf_rn(t[c][2], cr[j >> 1], acc);
+            const unsigned b = to_u8_trunc(acc);
+            if (j < 4) lo[c] |= b << (8 * j);
+            else hi[c] |= b << (8 * (j - 4));
+          }
+        }
+        const size_t off = (size_t)y * P.W + (size_t)sg * 8;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) *reinterpret_cast<uint2*>(o + c * hw + off) = make_uint2(lo[c], hi[c]);
+      }
+    }
+  }
+}
+#endif  // LRFB_SIM
+
 // exact sum of squared differences per image: integer arithmetic, order-independent
 __global__ void __launch_bounds__(256)
 sse_u8_kernel(const unsigned char* __restrict__ a, const unsigned char* __restrict__ b, long long per_img,

@@ -831,6 +831,14 @@ LRFB_EXPORT int32_t lrfb_qmf_decode(const lrfb_qmf_config* cfg, int32_t batch, c
   if (fast8_geometry(g, d_images) && g.lay.record_bytes % 8 == 0 && ((uintptr_t)d_factors % 8) == 0 &&
       g.lay.v_offset[0] % 8 == 0 && g.lay.v_offset[1] % 4 == 0 && g.lay.v_offset[2] % 4 == 0) {
     long long items = hw / 8;
+#ifndef LRFB_SIM
+    if (fused8_geometry(cfg, g, d_images) && g.lay.rank[0] <= 4 && g.lay.rank[1] <= 4 && g.lay.rank[2] <= 4 &&
+        !getenv("LRFB_DECODE_V1")) {
+      dim3 grid2((unsigned)std::min<long long>((items / 2 + 255) / 256, 4096), std::min(batch, 65535));
+      LRFB_LAUNCH(qmf_decode8x2_kernel, grid2, dim3(256), 0, (cudaStream_t)(uintptr_t)stream, d_factors, d_images, P);
+      return check_launch("qmf_decode8x2_kernel");
+    }
+#endif
     dim3 grid8((unsigned)std::min<long long>((items + 255) / 256, 4096), std::min(batch, 65535));
     LRFB_LAUNCH(qmf_decode8_kernel, grid8, dim3(256), 0, (cudaStream_t)(uintptr_t)stream, d_factors, d_images, P);
     return check_launch("qmf_decode8_kernel");

@@ -238,3 +238,29 @@ def test_eval_compression_mirror(manifest):
     assert abs(out["PSNR (dB)"] - e["psnr"]) < 0.05 and abs(out["bit rate (bpp)"] - e["bpp"]) < 0.02 * e["bpp"]
     b = lrf_b200.eval_qmf_batch(torch.stack([img, img]), **README_KW)
     assert abs(float(b["PSNR (dB)"][1]) - out["PSNR (dB)"]) < 1e-4
+
+
+@pytest.mark.parametrize("shape,rank", [((128, 192), None), ((256, 384), (3, 1, 2)), ((512, 768), None)])
+def test_decode_kernels_agree(monkeypatch, shape, rank):
+    """The int8-dot-product decoder (unpadded geometry, ranks <= 4) and the per-row float decoder give the same
+    pixels, for full-range random factors as well as for encoded images."""
+    import lrf_b200
+    from lrf_b200 import compression
+
+    H, W = shape
+    imgs = torch.stack([port.s_nat(2000 + i, H, W) for i in range(3)]).cuda()
+    kw = dict(README_KW)
+    if rank is not None:
+        kw.pop("quality")
+        kw["rank"] = rank
+    rec, lay, _ = lrf_b200.qmf_encode_batch(imgs, return_records=True, **kw)
+    cfg, _ = compression.resolve_plan(H, W, kw.get("rank"), kw.get("quality"), "YCbCr", (0.5, 0.5), (8, 8), (-16, 15), 10)
+    g = torch.Generator().manual_seed(5)
+    noise = torch.randint(-128, 128, rec.shape, generator=g, dtype=torch.int8).cuda()  # any int8 factors must agree
+    for records in (rec, noise):
+        monkeypatch.delenv("LRFB_DECODE_V1", raising=False)
+        fast = compression.decode_records(records, cfg)
+        monkeypatch.setenv("LRFB_DECODE_V1", "1")
+        slow = compression.decode_records(records, cfg)
+        monkeypatch.delenv("LRFB_DECODE_V1", raising=False)
+        assert torch.equal(fast, slow)
