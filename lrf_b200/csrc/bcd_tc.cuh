@@ -220,20 +220,23 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
     }
     __syncthreads();
     TC_TRACE_S(1)
-    for (int c = tid; c < kTcRows * (N / 4); c += NT) {
-      const int row = c >> 4, ch = c & 15;
-      float* dst = &sm.x[row * N + ((ch ^ (row & 7)) << 2)];
-      if (row < rows_here) cp_async16(dst, X + (size_t)(row0 + row) * N + ch * 4);
-      else dst[0] = dst[1] = dst[2] = dst[3] = 0.0f;
+    // three commit groups of ROWS/3 rows: the fixed-point conversion of a group starts as soon as it has landed
+    constexpr int kGroups = 3, kGroupRows = kTcRows / kGroups;
+    static_assert(kTcRows % (kGroups * 64) == 0, "row groups are whole 64-row conversion chunks");
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g) {
+      for (int c = tid; c < kGroupRows * (N / 4); c += NT) {
+        const int row = g * kGroupRows + (c >> 4), ch = c & 15;
+        float* dst = &sm.x[row * N + ((ch ^ (row & 7)) << 2)];
+        if (row < rows_here) cp_async16(dst, X + (size_t)(row0 + row) * N + ch * 4);
+        else dst[0] = dst[1] = dst[2] = dst[3] = 0.0f;
+      }
+      cp_async_commit();
     }
-    cp_async_commit();
     const float* Uinit = P.U + (size_t)mat * M * R + (size_t)row0 * R;
     TC_TRACE_S(2)
     gram_small<N, R>(sm.v, sm.b, tid);
     TC_TRACE_S(3)
-    cp_async_wait<0>();
-    __syncthreads();
-    TC_TRACE_S(4)
 
     // ---- Q8.24 byte planes of X into tensor memory (A operand of the V-phase MMAs) ----
     {
@@ -245,7 +248,15 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
       const unsigned sel = (1u - a_lo) | ((5u - a_lo) << 4);
       const unsigned lane_addr = tmem + ((unsigned)((warp & 3) * 32) << 16);
       const int sharers = (NW - (warp & 3) + 3) / 4;  // warps that own this TMEM lane quarter
+#pragma unroll
+      for (int g = 0; g < kGroups; ++g) {
+        if (g == 0) cp_async_wait<2>();
+        else if (g == 1) cp_async_wait<1>();
+        else cp_async_wait<0>();
+        __syncthreads();
+        if (g == 0) { TC_TRACE_S(4) }
       for (int ch = warp >> 2; ch < kTcRows / 64; ch += sharers) {  // 64 rows (16 cells) per store
+        if (ch / (kGroupRows / 64) != g) continue;
         unsigned w0[16], w1[16];
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
@@ -263,6 +274,7 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
         }
         tmem_st16(lane_addr + ch * 16, w0);
         tmem_st16(lane_addr + kTcColsA + ch * 16, w1);
+      }
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
