@@ -314,11 +314,18 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
             for (int r = 0; r < RP; ++r) acc2[i][r] = make_float2(0.0f, 0.0f);
 #pragma unroll
           for (int k4 = 0; k4 < N / 4; ++k4) {
+            // the 4 x R values of V for these 4 k's are contiguous: R 16-byte loads (R = 2: two k's per load)
+            float vflat[4 * R];
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+              const float4 t4 = *reinterpret_cast<const float4*>(&sm.v[k4 * 4 * R + 4 * q]);
+              vflat[4 * q] = t4.x, vflat[4 * q + 1] = t4.y, vflat[4 * q + 2] = t4.z, vflat[4 * q + 3] = t4.w;
+            }
             float2 vk[4][RP];
 #pragma unroll
             for (int k = 0; k < 4; ++k)
 #pragma unroll
-              for (int r = 0; r < RP; ++r) vk[k][r] = *reinterpret_cast<const float2*>(&sm.v[(k4 * 4 + k) * R + 2 * r]);
+              for (int r = 0; r < RP; ++r) vk[k][r] = make_float2(vflat[k * R + 2 * r], vflat[k * R + 2 * r + 1]);
 #pragma unroll
             for (int i = 0; i < RT; ++i) {
               const int row = tid + i * NT;
