@@ -173,7 +173,7 @@ bcd_resident_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
 #pragma unroll
             for (int r = 0; r < R; ++r) f[r] = bf16_to(sm.u[row * R + r]);
           }
-          gs_row<R>(f, acc[i], sm.b, t2_native_u, P.lo, P.hi);
+          gs_row_auto<R>(f, acc[i], sm.b, P.x_u8_range != 0, t2_native_u, P.lo, P.hi);
 #pragma unroll
           for (int r = 0; r < R; ++r) sm.u[row * R + r] = bf16_of(ok ? f[r] : 0.0f);
           if (ok) {
@@ -288,7 +288,7 @@ bcd_resident_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
         float f[R], A[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) f[r] = sm.v[n * R + r], A[r] = sm.a2[n * R + r];
-        gs_row<R>(f, A, sm.b2, t2_native_v, P.lo, P.hi);
+        gs_row_auto<R>(f, A, sm.b2, P.x_u8_range != 0, t2_native_v, P.lo, P.hi);
 #pragma unroll
         for (int r = 0; r < R; ++r) sm.v[n * R + r] = f[r];
       }

@@ -88,35 +88,6 @@ __device__ __forceinline__ void push_4x32(unsigned remote, int a, int b, int c, 
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
-// Division by a denominator that is shared by many numerators: the denominator-only half of __fdiv_rn's fast path
-// (MUFU.RCP + one Newton step) is hoisted, each quotient costs FMUL + 2 FFMA and is bit-identical to __fdiv_rn for
-// den in [1e-16, 1e10], |num| in {0} U [1e-17, 1e16] (tools/probes/fdiv_probe.cu: 0 mismatches in 1.4e11 divisions) —
-// a superset of what the sweeps produce from planes in [0, 256) and int8 bounds.
-__device__ __forceinline__ float rcp_refined(float den) {
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(den));
-  return __fmaf_rn(r, __fmaf_rn(-den, r, 1.0f), r);
-}
-__device__ __forceinline__ float div_prepared(float num, float den, float rcp) {
-  const float q0 = __fmul_rn(num, rcp);
-  return __fmaf_rn(rcp, __fmaf_rn(-den, q0, num), q0);
-}
-// gs_row (bcd.cuh) with the R divisions prepared: den[r] = B[r][r] + eps, rcp[r] = rcp_refined(den[r])
-template <int R>
-__device__ __forceinline__ void gs_row_prepared(float (&f)[R], const float (&A)[R], const float* __restrict__ B,
-                                                const float (&den)[R], const float (&rcp)[R], bool native, float lo,
-                                                float hi) {
-  if (R == 1) {
-    f[0] = qmf_project(div_prepared(__fadd_rn(A[0], kEps), den[0], rcp[0]), lo, hi);
-    return;
-  }
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const float num = __fsub_rn(A[r], gs_term2<R>(f, B, r, native));
-    f[r] = qmf_project(div_prepared(__fadd_rn(num, kEps), den[r], rcp[r]), lo, hi);
-  }
-}
-
 // two independent single-rounded FMAs in one issue slot (FFMA2 with a broadcast scalar operand): bit-identical to
 // fmaf(x, b.x, c.x) and fmaf(x, b.y, c.y)
 __device__ __forceinline__ float2 ffma2_bcast(float x, float2 b, float2 c) {
