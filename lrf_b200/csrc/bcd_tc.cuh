@@ -418,7 +418,8 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
           for (int r = 0; r < R; ++r) {
             if (!ok) f[r] = 0.0f;
             uown[i][r] = f[r];
-            sm.ub[(row >> 4) * 128 + r * 16 + (row & 15)] = (unsigned char)(signed char)(int)f[r];
+            // f is an integer in [-128, 127]: its two's-complement byte is the low mantissa byte of f + 1.5 * 2^23
+            sm.ub[(row >> 4) * 128 + r * 16 + (row & 15)] = (unsigned char)__float_as_uint(__fadd_rn(f[r], 12582912.0f));
           }
           // ---- V-phase on the tensor core, issued per 32-row chunk as soon as the chunk is projected (the MMAs of
           //      chunk i run under the Gauss–Seidel arithmetic of chunk i+1): D_a += S_a^T U, D_3 += U^T U ----
