@@ -413,7 +413,9 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
 #pragma unroll
             for (int r = 0; r < R; ++r) f[r] = uown[i][r];
           }
-          gs_row_prepared<R>(f, acc[i], breg, uden, urcp, t2_native_u, P.lo, P.hi);
+          // (one uniform branch per row instead of one per column: the flag is a compile-time constant inside)
+          if (t2_native_u) gs_row_prepared<R>(f, acc[i], breg, uden, urcp, true, P.lo, P.hi);
+          else gs_row_prepared<R>(f, acc[i], breg, uden, urcp, false, P.lo, P.hi);
 #pragma unroll
           for (int r = 0; r < R; ++r) {
             if (!ok) f[r] = 0.0f;
