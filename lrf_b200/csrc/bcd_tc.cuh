@@ -16,6 +16,9 @@
 #pragma once
 #include "bcd_resident.cuh"
 #include "gram_i8.cuh"
+#ifndef LRFB_SIM
+#include <cuda.h>  // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
+#endif
 
 #ifndef LRFB_SIM
 
@@ -46,7 +49,7 @@ struct TcSmem {
   alignas(16) longlong2 srecv[128];     // [source rank][owned column][r pair]: Q.24 sums of X^T U
   alignas(16) int4 grecv[kTcMaxCluster * 4];  // [source rank][j]: row j of that rank's U^T U
   alignas(16) float4 vrecv[N];          // gathered new rows of V (padded to 4 columns)
-  unsigned long long mma_done, clear_done, full, vfull;
+  unsigned long long mma_done, clear_done, full, vfull, xfull[3];
   unsigned tmem_base;
   int next_mat;                         // rank 0: matrix index drawn for the whole cluster
 };
@@ -110,6 +113,14 @@ __device__ __forceinline__ void umma_i8_ts(unsigned tmem_d, unsigned tmem_a, uns
       : "memory");
 }
 
+// X rows in shared memory: two half planes [half][row][32 floats] in TMA's 128-byte swizzle (16-byte chunk c of a row
+// sits at c ^ (row & 7)): what cp.async.bulk.tensor with CU_TENSOR_MAP_SWIZZLE_128B writes, and conflict-free both for
+// the row-per-thread 16-byte reads of the U half-sweep and the column reads of the fixed-point conversion.
+template <int ROWS>
+__device__ __forceinline__ int x_off(int row, int ch /* 16-byte chunk 0..15 of the 64-float row */) {
+  return (ch >> 3) * ROWS * 32 + row * 32 + (((ch & 7) ^ (row & 7)) << 2);
+}
+
 #ifdef LRFB_TC_TRACE
 __device__ long long g_tc_trace[16 * 12];  // probe build only (tools/probes/tc_trace.cu): clock64 at 9 points of every sweep
 #define TC_TRACE(pt) \
@@ -126,7 +137,7 @@ template <int R, int ROWS, int NT>
 // 2,2,1,1 on the four scheduler partitions, so two CTAs put 4 warps on one partition's 16K registers: <= 128 registers
 // per thread (bound declared as 256 threads x 2 CTAs).
 __global__ void __launch_bounds__((ROWS <= 384 ? 256 : NT), (ROWS <= 384 ? 2 : 1))
-bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
+bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta, const __grid_constant__ CUtensorMap x_map, int use_tma) {
   constexpr int N = 64, RT = ROWS / NT, NW = NT / 32;
   constexpr int kTcRows = ROWS;
   constexpr int kTcColsA = ROWS / 4;                        // TMEM columns per A block (4 rows per cell)
@@ -147,7 +158,7 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
   const bool from_a = P.s0 != nullptr;
   const int row0 = crank * rows_per_cta;
   const int rows_here = max(0, min(rows_per_cta, M - row0));
-  unsigned mma_phase = 0, full_phase = 0;
+  unsigned mma_phase = 0, full_phase = 0, x_phase = 0;
   const int npr = N / cluster_size, npr_log = 6 - (31 - __clz(cluster_size));  // columns of V owned per rank
   int sweeps_done = 0;
 #ifdef LRFB_TC_TRACE
@@ -159,6 +170,7 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
     mbar_init(&sm.clear_done, 1);
     mbar_init(&sm.full, 1);       // one arrive.expect_tx per sweep + the bytes of all ranks' pushes
     mbar_init(&sm.vfull, 1);
+    for (int g = 0; g < 3; ++g) mbar_init(&sm.xfull[g], 1);  // TMA: expect_tx + the bytes of one row group
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -220,18 +232,38 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
     }
     __syncthreads();
     TC_TRACE_S(1)
-    // three commit groups of ROWS/3 rows: the fixed-point conversion of a group starts as soon as it has landed
+    // three groups of ROWS/3 rows: the fixed-point conversion of a group starts as soon as it has landed.  TMA path:
+    // one thread issues 2 tensor copies (32 columns x 256 rows, 32 KB) per group, rows past M are zero-filled by the
+    // hardware (rows past this CTA's slice but inside M are loaded and ignored: their U rows are forced to zero).
     constexpr int kGroups = 3, kGroupRows = kTcRows / kGroups;
     static_assert(kTcRows % (kGroups * 64) == 0, "row groups are whole 64-row conversion chunks");
+    if (use_tma) {
+      if (tid == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of x vs the async writes
 #pragma unroll
-    for (int g = 0; g < kGroups; ++g) {
-      for (int c = tid; c < kGroupRows * (N / 4); c += NT) {
-        const int row = g * kGroupRows + (c >> 4), ch = c & 15;
-        float* dst = &sm.x[row * N + ((ch ^ (row & 7)) << 2)];
-        if (row < rows_here) cp_async16(dst, X + (size_t)(row0 + row) * N + ch * 4);
-        else dst[0] = dst[1] = dst[2] = dst[3] = 0.0f;
+        for (int g = 0; g < kGroups; ++g) {
+          const unsigned bar = smem_u32(&sm.xfull[g]);
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kGroupRows * 256) : "memory");
+#pragma unroll
+          for (int half = 0; half < 2; ++half)
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::
+                    "r"(smem_u32(&sm.x[half * kTcRows * 32 + g * kGroupRows * 32])),
+                "l"(reinterpret_cast<unsigned long long>(&x_map)), "r"(half * 32), "r"(row0 + g * kGroupRows), "r"(mat), "r"(bar)
+                : "memory");
+        }
       }
-      cp_async_commit();
+    } else {
+#pragma unroll
+      for (int g = 0; g < kGroups; ++g) {
+        for (int c = tid; c < kGroupRows * (N / 4); c += NT) {
+          const int row = g * kGroupRows + (c >> 4), ch = c & 15;
+          float* dst = &sm.x[x_off<ROWS>(row, ch)];
+          if (row < rows_here) cp_async16(dst, X + (size_t)(row0 + row) * N + ch * 4);
+          else dst[0] = dst[1] = dst[2] = dst[3] = 0.0f;
+        }
+        cp_async_commit();
+      }
     }
     const float* Uinit = P.U + (size_t)mat * M * R + (size_t)row0 * R;
     TC_TRACE_S(2)
@@ -250,10 +282,14 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
       const int sharers = (NW - (warp & 3) + 3) / 4;  // warps that own this TMEM lane quarter
 #pragma unroll
       for (int g = 0; g < kGroups; ++g) {
-        if (g == 0) cp_async_wait<2>();
-        else if (g == 1) cp_async_wait<1>();
-        else cp_async_wait<0>();
-        __syncthreads();
+        if (use_tma) {
+          mbar_wait(&sm.xfull[g], x_phase);
+        } else {
+          if (g == 0) cp_async_wait<2>();
+          else if (g == 1) cp_async_wait<1>();
+          else cp_async_wait<0>();
+          __syncthreads();
+        }
         if (g == 0) { TC_TRACE_S(4) }
       for (int ch = warp >> 2; ch < kTcRows / 64; ch += sharers) {  // 64 rows (16 cells) per store
         if (ch / (kGroupRows / 64) != g) continue;
@@ -264,7 +300,7 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             const int m = ch * 64 + c * 4 + t;
-            const float xv = sm.x[m * N + (((n >> 2) ^ (m & 7)) << 2) + (n & 3)];
+            const float xv = sm.x[x_off<ROWS>(m, n >> 2) + (n & 3)];
             const float h = __fmaf_rz(xv, 256.0f, 8388608.0f);                       // 2^23 + floor(256 x)
             const float frac = __fmaf_rn(xv, 256.0f, -__fadd_rn(h, -8388608.0f));     // exact, in [0, 1)
             yh[t] = __float_as_uint(h), yl[t] = __float_as_uint(__fmaf_rz(frac, 65536.0f, 8388608.0f));
@@ -277,6 +313,7 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
       }
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      x_phase ^= 1;
     }
     TC_TRACE_S(5)
     // the first kReg A-phase rows of this thread stay in registers for all sweeps
@@ -289,7 +326,7 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
       const int row = tid + i * NT;
 #pragma unroll
       for (int k4 = 0; k4 < N / 4; ++k4) {
-        const float4 t4 = *reinterpret_cast<const float4*>(&sm.x[row * N + ((k4 ^ (row & 7)) << 2)]);
+        const float4 t4 = *reinterpret_cast<const float4*>(&sm.x[x_off<ROWS>(row, k4)]);
         xr[i][(4 * k4 + 0) % kRegN] = t4.x, xr[i][(4 * k4 + 1) % kRegN] = t4.y;
         xr[i][(4 * k4 + 2) % kRegN] = t4.z, xr[i][(4 * k4 + 3) % kRegN] = t4.w;
       }
@@ -336,7 +373,7 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
                 xv = make_float4(xr[ii][(4 * k4 + 0) % kRegN], xr[ii][(4 * k4 + 1) % kRegN],
                                  xr[ii][(4 * k4 + 2) % kRegN], xr[ii][(4 * k4 + 3) % kRegN]);
               } else {
-                xv = *reinterpret_cast<const float4*>(&sm.x[row * N + ((k4 ^ (row & 7)) << 2)]);
+                xv = *reinterpret_cast<const float4*>(&sm.x[x_off<ROWS>(row, k4)]);
               }
 #pragma unroll
               for (int r = 0; r < RP; ++r) {
@@ -375,7 +412,7 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta) {
               xv = make_float4(xr[ii][(4 * k4 + 0) % kRegN], xr[ii][(4 * k4 + 1) % kRegN],
                                xr[ii][(4 * k4 + 2) % kRegN], xr[ii][(4 * k4 + 3) % kRegN]);
             } else {
-              xv = *reinterpret_cast<const float4*>(&sm.x[row * N + ((k4 ^ (row & 7)) << 2)]);
+              xv = *reinterpret_cast<const float4*>(&sm.x[x_off<ROWS>(row, k4)]);
             }
 #pragma unroll
             for (int r = 0; r < R; ++r) {

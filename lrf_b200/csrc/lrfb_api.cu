@@ -255,6 +255,33 @@ int launch_bcd_resident_cfg(const BcdBatch& b, cudaStream_t st) {
 
 #ifndef LRFB_SIM
 // resident sweeps with the V-phase on tcgen05 (int8, A operand in TMEM): N = 64, R <= 4, X in [0, 256)
+// 3-D tensor map over X [n_mat][M][64] f32 with a 32-column x 256-row box and the 128-byte swizzle (see x_off in
+// bcd_tc.cuh).  The encoder lives in the driver library: fetched through the runtime, no link-time dependency.
+bool make_x_tensor_map(const BcdBatch& b, CUtensorMap* out) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  static bool looked = false;
+  if (!looked) {
+    looked = true;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (!getenv("LRFB_NO_TMA") &&
+        cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      encode = reinterpret_cast<EncodeFn>(fn);
+    cudaGetLastError();
+  }
+  if (!encode || (reinterpret_cast<uintptr_t>(b.X) & 15) || ((b.x_stride * 4) & 15)) return false;
+  const cuuint64_t dims[3] = {64, (cuuint64_t)b.M, (cuuint64_t)b.n_mat};
+  const cuuint64_t strides[2] = {256, (cuuint64_t)b.x_stride * 4};
+  const cuuint32_t box[3] = {32, 256, 1}, estr[3] = {1, 1, 1};
+  return encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(b.X), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int R, int ROWS, int NT>
 int launch_bcd_tc_cfg(const BcdBatch& b, cudaStream_t st) {
   const int need = (b.M + ROWS - 1) / ROWS;
@@ -303,7 +330,10 @@ int launch_bcd_tc_cfg(const BcdBatch& b, cudaStream_t st) {
   if (getenv("LRFB_DEBUG"))
     fprintf(stderr, "[lrfb] bcd_tc R=%d rows/cta=%d threads=%d cluster=%d max_active_clusters=%d grid=%u smem=%zu\n",
             R, ROWS, NT, csize, max_clusters, cfg.gridDim.x, smem);
-  e = cudaLaunchKernelEx(&cfg, kern, b, csize, rows_per_cta);
+  CUtensorMap x_map;
+  memset(&x_map, 0, sizeof(x_map));
+  const int use_tma = (ROWS == 768 && make_x_tensor_map(b, &x_map)) ? 1 : 0;  // box rows = ROWS / 3 = 256
+  e = cudaLaunchKernelEx(&cfg, kern, b, csize, rows_per_cta, x_map, use_tma);
   if (e != cudaSuccess) return fail((int)e, "bcd_tc launch: %s", cudaGetErrorString(e));
   return check_launch("bcd_tc_kernel");
 }

@@ -40,7 +40,8 @@ int main(int argc, char** argv) {
   cfg.blockDim = dim3(nt), cfg.dynamicSmemBytes = smem, cfg.attrs = attr, cfg.numAttrs = 1, cfg.gridDim = dim3(chroma ? 148 : small ? 224 : 120);
   for (int rep = 0; rep < 2; ++rep) {
     cudaMemset(counter, 0, 4);
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, b, csize, rows);
+    CUtensorMap x_map = {};
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, b, csize, rows, x_map, 0);
     cudaError_t e2 = cudaDeviceSynchronize();
     if (e != cudaSuccess || e2 != cudaSuccess) { printf("error %s %s\n", cudaGetErrorString(e), cudaGetErrorString(e2)); return 1; }
   }
