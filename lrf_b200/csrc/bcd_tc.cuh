@@ -638,7 +638,9 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta, const __grid_const
       }
     }
   }
-  // (the loop exits right after a cluster.sync that followed the last exchange: nobody is written to after exit)
+  // The loop exits right after a cluster.sync that followed the last exchange, so nobody is written to after exit; but
+  // every CTA has just READ rank 0's matrix index through DSMEM, and rank 0 must not exit before those reads.
+  cluster.sync();
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
