@@ -20,10 +20,17 @@ struct DecodeParams {
   long long u_off[3], v_off[3];
 };
 
-__device__ __forceinline__ unsigned char to_u8_trunc(float v) {
+// clamp to [0, 255], then truncate.  On the device the truncation is a round-toward-zero add onto 2^23 (the integer
+// part lands in the low mantissa bits): full-rate FADD instead of the quarter-rate F2I that bounded the decoder.
+__device__ __forceinline__ unsigned to_u8_bits(float v) {  // result in the low byte
   v = fminf(fmaxf(v, 0.0f), 255.0f);
-  return (unsigned char)(int)v;
+#ifdef LRFB_SIM
+  return (unsigned)(int)v;
+#else
+  return __float_as_uint(__fadd_rz(v, 8388608.0f)) & 0xffu;
+#endif
 }
+__device__ __forceinline__ unsigned char to_u8_trunc(float v) { return (unsigned char)to_u8_bits(v); }
 
 __device__ __forceinline__ float plane_value(const int8_t* __restrict__ rec, const DecodeParams& P, int c,
                                              int chan, int y, int x) {
@@ -234,7 +241,7 @@ qmf_decode8x2_kernel(const int8_t* __restrict__ factors, unsigned char* __restri
         unsigned wl[4], wh[4];
         transpose4x4_bytes(vr[0].x, vr[1].x, vr[2].x, vr[3].x, wl);
         transpose4x4_bytes(vr[0].y, vr[1].y, vr[2].y, vr[3].y, wh);
-        unsigned lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+        unsigned px[3][8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float yv = (float)__dp4a((int)(j < 4 ? wl[j & 3] : wh[j & 3]), (int)uw, 0);
@@ -243,14 +250,17 @@ qmf_decode8x2_kernel(const int8_t* __restrict__ factors, unsigned char* __restri
             float acc = __fmul_rn(t[c][0], yv);
             acc = __fmaf_rn(t[c][1], cb[j >> 1], acc);
             acc = __fmaf_rn(t[c][2], cr[j >> 1], acc);
-            const unsigned b = to_u8_trunc(acc);
-            if (j < 4) lo[c] |= b << (8 * j);
-            else hi[c] |= b << (8 * (j - 4));
+            acc = fminf(fmaxf(acc, 0.0f), 255.0f);
+            px[c][j] = __float_as_uint(__fadd_rz(acc, 8388608.0f));  // pixel value in the low byte
           }
         }
         const size_t off = (size_t)y * P.W + (size_t)sg * 8;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) *reinterpret_cast<uint2*>(o + c * hw + off) = make_uint2(lo[c], hi[c]);
+        for (int c = 0; c < 3; ++c) {  // low bytes of 4 words -> one word: 3 PRMT
+          const unsigned lo = __byte_perm(__byte_perm(px[c][0], px[c][1], 0x0040), __byte_perm(px[c][2], px[c][3], 0x0040), 0x5410);
+          const unsigned hi = __byte_perm(__byte_perm(px[c][4], px[c][5], 0x0040), __byte_perm(px[c][6], px[c][7], 0x0040), 0x5410);
+          *reinterpret_cast<uint2*>(o + c * hw + off) = make_uint2(lo, hi);
+        }
       }
     }
   }
