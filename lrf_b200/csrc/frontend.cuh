@@ -184,10 +184,18 @@ frontend8_chroma_kernel(const unsigned char* __restrict__ images, float* __restr
         }
       }
       const float kh = (float)(h1 - h0);
+      if (h1 - h0 == 2) {  // the usual window: dividing by 2 is an exact scaling, two multiplies give the same bits
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        sb[j] = __fdiv_rn(__fdiv_rn(sb[j], kh), 2.0f);
-        sr[j] = __fdiv_rn(__fdiv_rn(sr[j], kh), 2.0f);
+        for (int j = 0; j < 8; ++j) {
+          sb[j] = __fmul_rn(__fmul_rn(sb[j], 0.5f), 0.5f);
+          sr[j] = __fmul_rn(__fmul_rn(sr[j], 0.5f), 0.5f);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          sb[j] = __fmul_rn(__fdiv_rn(sb[j], kh), 0.5f);
+          sr[j] = __fmul_rn(__fdiv_rn(sr[j], kh), 0.5f);
+        }
       }
       const size_t o = ((size_t)(yy >> 3) * nbw + wb) * 64 + (yy & 7) * 8;
       *reinterpret_cast<float4*>(ocb + o) = make_float4(sb[0], sb[1], sb[2], sb[3]);
