@@ -18,9 +18,9 @@ namespace lrfb {
 
 constexpr int kEigMaxR = 32;
 
-struct EigScratch {  // per matrix (doubles): d, e, tau, vv, w [5N] | lam [32] | z [R][N] | lu [R][5N]
+struct EigScratch {  // per matrix (doubles): d, e, tau, vv, w [5N] | lam [32] | z [R][N] | lu [R][5N] | g4, p4 [8N]
   static __host__ __device__ size_t doubles(int N, int R) {
-    return (size_t)5 * N + kEigMaxR + (size_t)R * N + (size_t)R * 5 * N + 8;
+    return (size_t)5 * N + kEigMaxR + (size_t)R * N + (size_t)R * 5 * N + 8 + (size_t)8 * N;
   }
   static __host__ __device__ bool fits_shared(int N, int R) { return N == 64 && R <= 4; }
 };
@@ -140,6 +140,130 @@ __device__ inline void tridiag_inverse_iteration(const double* d, const double* 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Column signs of the right singular vectors as LAPACK's gesdd returns them (lrf/factorization/qmf.py:44 takes
+// torch.linalg.svd's signs as they come, and a flipped (u_r, v_r) pair saturates differently against asymmetric
+// bounds, so the encoded bytes depend on them).  For a tall matrix (gesdd: QR -> gebrd -> bdsdc) the signs of the
+// dominant vectors are a closed-form function of G = X^T X and the top-left R x R block of X
+// (tools/research/lapack_sign_rule.py validates every step against MKL sgesdd and netlib dgesdd):
+//   * V = PB V_B, and PB (right reflectors of gebrd on the QR factor) is exactly the orthogonal factor of the
+//     e_1-preserving Householder tridiagonalisation of G that this solver performs anyway: p_l = G_0..G_{l-1} e_l;
+//   * the dominant singular vectors of the bidiagonal B live in the leading coordinates (Lanczos convergence), bdsdc
+//     deflates them at every merge, so their signs are those of the implicit-QR leaf solver (bdsqr), whose limit obeys the
+//     leading-principal-minor rule: det VB[0..i][0..i] / det VB[0..i-1][0..i-1] has the sign of d_i, the i-th diagonal
+//     entry of B before bdsqr makes the singular values positive by flipping rows of V^T;
+//   * sign d_i = D_i * S_i: D_i = sign of the i-th diagonal entry of the Householder-QR factor of X (a function of the
+//     first R rows of the first R columns of X and of G[0..R)[0..R) only: everything below enters through its Gram),
+//     S_i = sign of the i-th diagonal of gebrd's left Householder history on the Cholesky factor C of G, which needs
+//     z_l = C p_l only through its first R components and the Gram <z_j, z_l> = T[j][l] (the tridiagonal).
+// Near-degenerate spectra (S-iid noise images) fall outside the premise; the rule is then as arbitrary as any other.
+struct SignIn {
+  double g4[4][4];  // G[0..4)[0..4)
+  double x4[4][4];  // X[0..4)[0..4)
+  double zt[4][4];  // zt[i][l] = (C p_l)[i], C = upper Cholesky factor of G
+  double td[4], te[4];  // leading tridiagonal: diagonal, sub-diagonal (LAPACK's signs)
+  double vb[4][4];  // vb[l][j] = <p_l, v_j>
+};
+
+// signs of the first R diagonal entries of the Householder-QR factor (dgeqr2 / dlarfg conventions) of a tall matrix
+// given its first R rows `top` (top[row][col]) and the R x R Gram matrix of its columns
+__device__ inline void house_diag_signs(const double (*top)[4], const double (*gram)[4], int R, bool first_col_exact,
+                                        double* sg) {
+  double Z[8][4];
+  double S[4][4];
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      double t = 0.0;
+      if (i < R && j < R) {
+        t = gram[i][j];
+        for (int k = 0; k < R; ++k) t -= top[k][i] * top[k][j];
+      }
+      S[i][j] = t;
+    }
+  if (first_col_exact)  // column 0 has nothing below its top entry (column 0 of a triangular factor)
+    for (int i = 0; i < 4; ++i) S[0][i] = S[i][0] = 0.0;
+  for (int i = 0; i < 8; ++i)
+    for (int j = 0; j < 4; ++j) Z[i][j] = (i < R && j < R) ? top[i][j] : 0.0;
+  for (int i = 0; i < R; ++i) {  // upper Cholesky factor of the remainder, non-positive pivots dropped
+    const double piv = S[i][i];
+    if (!(piv > 0.0)) continue;
+    const double rt = sqrt(piv);
+    for (int j = i; j < R; ++j) Z[R + i][j] = S[i][j] / rt;
+    for (int a = i + 1; a < R; ++a)
+      for (int b = i + 1; b < R; ++b) S[a][b] -= Z[R + i][a] * Z[R + i][b];
+  }
+  for (int k = 0; k < R; ++k) {
+    const double alpha = Z[k][k];
+    double xn2 = 0.0;
+    for (int i = k + 1; i < 2 * R; ++i) xn2 = fma(Z[i][k], Z[i][k], xn2);
+    if (xn2 == 0.0) {
+      sg[k] = alpha < 0.0 ? -1.0 : 1.0;
+      continue;
+    }
+    const double nrm = sqrt(fma(alpha, alpha, xn2));
+    const double beta = alpha >= 0.0 ? -nrm : nrm;
+    const double tau = (beta - alpha) / beta, scal = 1.0 / (alpha - beta);
+    sg[k] = beta < 0.0 ? -1.0 : 1.0;
+    for (int j = k + 1; j < R; ++j) {
+      double dot = Z[k][j];
+      for (int i = k + 1; i < 2 * R; ++i) dot = fma(Z[i][k] * scal, Z[i][j], dot);
+      dot *= tau;
+      Z[k][j] -= dot;
+      for (int i = k + 1; i < 2 * R; ++i) Z[i][j] = fma(-dot, Z[i][k] * scal, Z[i][j]);
+    }
+  }
+}
+
+__device__ inline double det_leading(const double (*m)[4], const double* colsign, int n) {  // n <= 4, partial pivoting
+  double a[4][4];
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) a[i][j] = m[i][j] * colsign[j];
+  double det = 1.0;
+  for (int k = 0; k < n; ++k) {
+    int p = k;
+    for (int i = k + 1; i < n; ++i)
+      if (fabs(a[i][k]) > fabs(a[p][k])) p = i;
+    if (a[p][k] == 0.0) return 0.0;
+    if (p != k) {
+      for (int j = 0; j < n; ++j) {
+        const double t = a[k][j];
+        a[k][j] = a[p][j], a[p][j] = t;
+      }
+      det = -det;
+    }
+    det *= a[k][k];
+    for (int i = k + 1; i < n; ++i) {
+      const double f = a[i][k] / a[k][k];
+      for (int j = k; j < n; ++j) a[i][j] = fma(-f, a[k][j], a[i][j]);
+    }
+  }
+  return det;
+}
+
+// flips[r] = +1 / -1 such that v_r * flips[r] carries LAPACK's sign (r < R <= 4)
+__device__ __noinline__ void lapack_sign_flips(const SignIn* in, int R, double* flips) {
+  double dq[4], dz[4], T[4][4];
+  house_diag_signs(in->x4, in->g4, R, false, dq);
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) T[i][j] = i == j ? in->td[i] : ((i == j + 1) ? in->te[j] : ((j == i + 1) ? in->te[i] : 0.0));
+  house_diag_signs(in->zt, T, R, true, dz);
+  double prev = 1.0;
+  for (int i = 0; i < 4; ++i) flips[i] = 1.0;
+  for (int i = 0; i < R; ++i) {
+    double m = det_leading(in->vb, flips, i + 1);
+    const double want = dq[i] * dz[i];
+    if (m != 0.0 && ((m < 0.0) != (prev < 0.0) ? -1.0 : 1.0) != want) flips[i] = -1.0, m = -m;
+    if (m != 0.0) prev = m;
+  }
+}
+
+// `tall`: gesdd takes the QR route for M >= 11N/6; the rule was validated down to M = 1.5 N.  Wide matrices (M < N) run
+// the transposed algorithm: only the dominant pair is predictable there (positive for non-negative planes).
+__device__ __forceinline__ bool sign_rule_applies(int M_rows, int N, int R) {
+  return R <= 4 && N >= 8 && 2 * M_rows >= 3 * N;
+}
+
 // One warp (= one CTA of 32 threads) per matrix.  Gin: [n][N][N] symmetric (overwritten when the
 // working copy stays in global memory).  Outputs per matrix: evec[N][R] (unit, sign-fixed, row-major)
 // and sigma[R] = sqrt(max(lambda, 0)).  sign_flip: optional [n][R] of +1/-1 multiplied onto the
@@ -151,7 +275,7 @@ __global__ void __launch_bounds__(32)
 eig_topr_kernel(const double* __restrict__ Gin, int Nrt, int R, double* __restrict__ scratch_all,
                 double* __restrict__ evec_out, double* __restrict__ sigma_out,
                 const int* __restrict__ sign_flip, int use_shared, int M_rows, float* __restrict__ v0_out,
-                float* __restrict__ s0_out) {
+                float* __restrict__ s0_out, const float* __restrict__ X, long long x_stride) {
   LRFB_DYN_SMEM(smem_raw);
   const int N = NC ? NC : Nrt;
   const int mat = blockIdx.x;
@@ -176,6 +300,12 @@ eig_topr_kernel(const double* __restrict__ Gin, int Nrt, int R, double* __restri
   double* lam = w + N;
   double* z = lam + kEigMaxR;
   double* lu = z + (size_t)R * N;
+  double* g4s = lu + (size_t)R * 5 * N;  // rows 0..3 of G (the tridiagonalisation overwrites them)
+  double* p4 = g4s + 4 * N;              // p_0..p_3: first columns of the tridiagonalising transformation
+  const bool emulate = X != nullptr && sign_rule_applies(M_rows, N, R);
+  __syncwarp();
+  if (emulate)
+    for (int i = lane; i < 4 * N; i += 32) g4s[i] = A[i];
   __syncwarp();
 
   // ---- 1. tridiagonalisation -------------------------------------------------------------------
@@ -357,14 +487,63 @@ eig_topr_kernel(const double* __restrict__ Gin, int Nrt, int R, double* __restri
   __syncwarp();
 
   // ---- 5. sign convention and output ------------------------------------------------------------
-  // LAPACK returns the Perron pair of a positive matrix with all-negative entries;
-  // for every component we pick the sign that makes sum(v) <= 0.  sign_flip overrides per column.
+  // Tall matrices: LAPACK's own signs (lapack_sign_flips).  Otherwise, and for rank-deficient input: the dominant
+  // pair of a non-negative matrix comes out of gesdd all-negative for M >= N and all-positive for M < N (measured);
+  // for the other components we pick sum(v) <= 0.  sign_flip (test hook) multiplies on top.
+  double* flips = lam + 8;  // lam has kEigMaxR >= 12 slots, R <= 4 here
+  if (emulate) {
+    if (lane == 0) {
+      SignIn in;
+      bool pd = true;
+      // first 4 rows of the upper Cholesky factor of G -> lu[i*N + c]
+      double* c4 = lu;
+      for (int i = 0; i < 4; ++i) {
+        double piv = g4s[i * N + i];
+        for (int j = 0; j < i; ++j) piv -= c4[j * N + i] * c4[j * N + i];
+        if (!(piv > 1e-12 * g4s[i * N + i])) pd = false, piv = 1.0;
+        const double rt = sqrt(piv);
+        for (int c = 0; c < N; ++c) {
+          double t = g4s[i * N + c];
+          for (int j = 0; j < i; ++j) t -= c4[j * N + i] * c4[j * N + c];
+          c4[i * N + c] = c >= i ? t / rt : 0.0;
+        }
+      }
+      for (int l = 0; l < 4; ++l) {  // p_l = G_0 .. G_{l-1} e_l
+        double* y = p4 + l * N;
+        for (int i = 0; i < N; ++i) y[i] = i == l ? 1.0 : 0.0;
+        for (int k = min(l, N - 2) - 1; k >= 0; --k) {
+          const double* hk = A + k * N;
+          double dot = 0.0;
+          for (int i = k + 1; i < N; ++i) dot = fma(hk[i], y[i], dot);
+          dot *= tau[k];
+          for (int i = k + 1; i < N; ++i) y[i] = fma(-dot, hk[i], y[i]);
+        }
+      }
+      for (int i = 0; i < 4; ++i)
+        for (int l = 0; l < 4; ++l) {
+          double t = 0.0, q = 0.0;
+          for (int c = 0; c < N; ++c) t = fma(c4[i * N + c], p4[l * N + c], t);
+          if (l < R)
+            for (int c = 0; c < N; ++c) q = fma(p4[i * N + c], z[l * N + c], q);
+          in.zt[i][l] = t, in.vb[i][l] = q;
+          in.g4[i][l] = g4s[i * N + l];
+          in.x4[i][l] = (i < M_rows && l < N) ? (double)X[(size_t)mat * x_stride + (size_t)i * N + l] : 0.0;
+        }
+      for (int i = 0; i < 4; ++i) in.td[i] = d[i], in.te[i] = e[i];
+      if (pd) lapack_sign_flips(&in, R, flips);
+      flips[4] = pd ? 1.0 : 0.0;
+    }
+    __syncwarp();
+  }
+  const bool have_flips = emulate && flips[4] != 0.0;
   for (int r = 0; r < R; ++r) {
     const double* zr = z + r * N;
     double part = 0.0;
     for (int i = lane; i < N; i += 32) part += zr[i];
     const double s = warp_sum(part);
     double sg = s > 0.0 ? -1.0 : 1.0;
+    if (r == 0 && M_rows < N) sg = -sg;
+    if (have_flips) sg = flips[r];
     if (sign_flip) sg *= (double)sign_flip[(size_t)mat * R + r];
     const double sig = sqrt(fmax(lam[r], 0.0));
     // SVDInit (lrf/factorization/qmf.py:45-52): keep min(R, M, N) triplets, v0 = V_R * sqrt(s) in f32
@@ -509,7 +688,10 @@ struct Eig64Smem {
   double red[8];
   double lam[4];
   double z[4 * 64];
-  double lu[4 * 5 * 64];
+  double lu[4 * 5 * 64];  // inverse iteration; afterwards p_0..p_3 (lu[0..256)) and 4 Cholesky rows (lu[256..512))
+  double g4[4 * 64];      // rows 0..3 of G, saved before the tridiagonalisation
+  SignIn sign_in;
+  double flips[8];
 };
 
 // one-barrier variant: the caller alternates `slot` (0/1) between consecutive uses, so a slow reader of one use never
@@ -540,7 +722,7 @@ __device__ long long g_eig_trace[8];  // probe build only (tools/probes/eig_trac
 __global__ void __launch_bounds__(64, 6)
 eig64_topr_kernel(double* __restrict__ G, int R, double* __restrict__ evec_out, double* __restrict__ sigma_out,
                   const int* __restrict__ sign_flip, int M_rows, float* __restrict__ v0_out,
-                  float* __restrict__ s0_out) {
+                  float* __restrict__ s0_out, const float* __restrict__ X, long long x_stride) {
   constexpr int N = 64;
   __shared__ Eig64Smem sm;
   const int mat = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -548,6 +730,9 @@ eig64_topr_kernel(double* __restrict__ G, int R, double* __restrict__ evec_out, 
   double a[N];  // column `tid`
 #pragma unroll
   for (int j = 0; j < N; ++j) a[j] = g[j * N + tid];
+  const bool emulate = X != nullptr && sign_rule_applies(M_rows, N, R);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) sm.g4[i * N + tid] = a[i];  // G[i][tid] = G[tid][i]
 
   EIG_TRACE(0)
   // ---- 1. tridiagonalisation ----
@@ -717,12 +902,73 @@ eig64_topr_kernel(double* __restrict__ G, int R, double* __restrict__ evec_out, 
   }
 
   EIG_TRACE(5)
-  // ---- 5. sign convention (sum(v) <= 0, see eig_topr_kernel) and output ----
+  // ---- 5. column signs (see lapack_sign_flips / eig_topr_kernel) and output ----
+  bool have_flips = false;
+  if (emulate) {  // uniform
+    // this thread's column of the first 4 rows of the upper Cholesky factor of G (leading 4 x 4 block redundantly)
+    double L[4][4], cc[4];
+    bool pd = true;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      double piv = sm.g4[i * N + i];
+#pragma unroll
+      for (int j = 0; j < i; ++j) piv = fma(-L[j][i], L[j][i], piv);
+      if (!(piv > 1e-12 * sm.g4[i * N + i])) pd = false, piv = 1.0;
+      const double rinv = 1.0 / sqrt(piv);
+#pragma unroll
+      for (int c = i + 1; c < 4; ++c) {
+        double t = sm.g4[i * N + c];
+#pragma unroll
+        for (int j = 0; j < i; ++j) t = fma(-L[j][i], L[j][c], t);
+        L[i][c] = t * rinv;
+      }
+      double t = sm.g4[i * N + tid];
+#pragma unroll
+      for (int j = 0; j < i; ++j) t = fma(-L[j][i], cc[j], t);
+      cc[i] = tid >= i ? t * rinv : 0.0;
+    }
+    // p_l = G_0 .. G_{l-1} e_l, element `tid` (a[k] = element tid of reflector k, 1 at tid == k + 1)
+    const double h0 = tid > 0 ? a[0] : 0.0, h1 = tid > 1 ? a[1] : 0.0, h2 = tid > 2 ? a[2] : 0.0;
+    const double t0 = sm.tau[0], t1 = sm.tau[1], t2 = sm.tau[2];
+    double pl[4];
+    pl[0] = tid == 0 ? 1.0 : 0.0;
+    pl[1] = fma(-t0, h0, tid == 1 ? 1.0 : 0.0);
+    double y = fma(-t1, h1, tid == 2 ? 1.0 : 0.0);
+    pl[2] = fma(-t0 * block64_sum(h0 * y, sm.red, tid), h0, y);
+    y = fma(-t2, h2, tid == 3 ? 1.0 : 0.0);
+    y = fma(-t1 * block64_sum(h1 * y, sm.red, tid), h1, y);
+    pl[3] = fma(-t0 * block64_sum(h0 * y, sm.red, tid), h0, y);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sm.lu[i * N + tid] = pl[i], sm.lu[256 + i * N + tid] = cc[i], sm.z[i * N + tid] = zc[i];
+    __syncthreads();
+    if (tid < 32) {  // 32 dot products of length 64, one per thread
+      const int i = (tid >> 2) & 3, l = tid & 3;
+      const double* aa = tid < 16 ? sm.lu + i * N : sm.lu + 256 + i * N;  // p_i | row i of C
+      const double* bb = tid < 16 ? sm.z + l * N : sm.lu + l * N;          // v_l | p_l
+      double q0 = 0.0, q1 = 0.0;
+#pragma unroll 8
+      for (int c = 0; c < N; c += 2) q0 = fma(aa[c], bb[c], q0), q1 = fma(aa[c + 1], bb[c + 1], q1);
+      if (tid < 16) sm.sign_in.vb[i][l] = q0 + q1;
+      else sm.sign_in.zt[i][l] = q0 + q1;
+    } else if (tid < 48) {
+      const int i = (tid >> 2) & 3, l = tid & 3;
+      sm.sign_in.g4[i][l] = sm.g4[i * N + l];
+      sm.sign_in.x4[i][l] = i < M_rows ? (double)X[(size_t)mat * x_stride + (size_t)i * N + l] : 0.0;
+    } else if (tid < 52) {
+      sm.sign_in.td[tid - 48] = sm.d[tid - 48], sm.sign_in.te[tid - 48] = sm.e[tid - 48];
+    }
+    __syncthreads();
+    if (tid == 0 && pd) lapack_sign_flips(&sm.sign_in, R, sm.flips);
+    __syncthreads();
+    have_flips = pd;
+  }
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     if (r >= R) break;
     const double s = block64_sum(zc[r], sm.red, tid);
     double sg = s > 0.0 ? -1.0 : 1.0;
+    if (r == 0 && M_rows < N) sg = -sg;
+    if (have_flips) sg = sm.flips[r];
     if (sign_flip) sg *= (double)sign_flip[(size_t)mat * R + r];
     const double sig = sqrt(fmax(sm.lam[r], 0.0));
     const bool kept = r < min(M_rows, N) && sig > 0.0;

@@ -512,13 +512,14 @@ int factorize_batch(const float* x, int n_mat, int M, int N, int R, float lo, fl
 #endif
     }
     if (use_shared && eig_v3)
-      LRFB_LAUNCH(eig64_topr_kernel, dim3(n_mat), dim3(64), 0, st, gram, R, evec, sigma, sign_flip, M, v, s0);
+      LRFB_LAUNCH(eig64_topr_kernel, dim3(n_mat), dim3(64), 0, st, gram, R, evec, sigma, sign_flip, M, v, s0, x,
+                  (long long)M * N);
     else if (use_shared)
       LRFB_LAUNCH(eig_topr_kernel<64>, dim3(n_mat), dim3(32), eig_smem, st, gram, N, R, eig_scratch, evec, sigma,
-                  sign_flip, use_shared, M, v, s0);
+                  sign_flip, use_shared, M, v, s0, x, (long long)M * N);
     else
       LRFB_LAUNCH(eig_topr_kernel<0>, dim3(n_mat), dim3(32), 0, st, gram, N, R, eig_scratch, evec, sigma,
-                  sign_flip, use_shared, M, v, s0);
+                  sign_flip, use_shared, M, v, s0, x, (long long)M * N);
     if ((rc = check_launch("eig_topr_kernel"))) return rc;
   }
   if (stop_after_init || phase == 1) return 0;

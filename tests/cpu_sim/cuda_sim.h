@@ -118,6 +118,7 @@ inline T exchange(T v, int src_lane) {  // every lane of the warp must call
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__ __attribute__((noinline))
 #define __shared__ static
 #define __launch_bounds__(...)
 #define __align__(n) alignas(n)

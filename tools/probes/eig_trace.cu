@@ -34,7 +34,7 @@ int main() {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0), cudaEventCreate(&e1);
     cudaEventRecord(e0);
-    eig64_topr_kernel<<<B, 64>>>(G, R, evec, sigma, nullptr, 6144, v0, s0);
+    eig64_topr_kernel<<<B, 64>>>(G, R, evec, sigma, nullptr, 6144, v0, s0, nullptr, 0);
     cudaEventRecord(e1);
     cudaError_t e = cudaDeviceSynchronize();
     float ms;
