@@ -9,6 +9,12 @@ factor records in HBM) over one batch; the batch is sharded across ranks with no
 (weak scaling: every rank owns a full per-GPU batch); NCCL only gathers per-image bpp / PSNR afterwards.
 Prints ONE JSON line on rank 0 (see the driver contract).  `--impl reference` times the reference's CPU
 implementation (the oracle port of it — /root/reference does not exist on the GPU box) on host cores.
+
+Besides the headline (`value`, `e2e`, `roofline`, `cpu_baseline`) the line carries, each with its own roofline
+fraction: `decode` (lrf.qmf_decode's device part), `clic` (configs[4]: 2048x1365 images, every N), `svd`
+(configs[2]), `ablation` (configs[3] end points), `e2e_bytes` (images on the host -> `bytes`, zlib included) and
+`quality.vs_reference` (the oracle port run here on a sample of the benchmarked images: dPSNR, dbytes, identical-bytes
+fraction through the public path, near-tie accounting).  `--quick` skips those extras.
 """
 from __future__ import annotations
 
@@ -104,6 +110,30 @@ def cuda_time_ms(fn, stream=None):
     return e0.elapsed_time(e1)
 
 
+def time_steps_ms(fn, steps, warmup):
+    """ms per call of fn: `warmup` untimed calls, then `steps` calls between CUDA events on the current stream."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    e1.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def qmf_flops_per_image(lay, iters):
+    """SURVEY.md §8(d) table with this geometry's M, N, R: colour + pool, Gram, projection, BCD sweeps."""
+    n = lay.cols
+    fl = 19.5 * lay.orig_h[0] * lay.orig_w[0]
+    for pl in range(lay.n_planes):
+        m, r = lay.rows[pl], lay.rank[pl]
+        fl += m * n * (n + 1) + 2 * m * n * r + iters * (4 * m * n * r + (m + n) * r * (4 * r + 4))
+    return fl
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -168,6 +198,11 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=512, help="images for the cpu_baseline leg")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="headline, e2e, roofline only")
+    ap.add_argument("--clic-batch", type=int, default=256, help="2048x1365 images per GPU for the clic leg")
+    ap.add_argument("--side-batch", type=int, default=256, help="images for the svd / ablation legs")
+    ap.add_argument("--bytes-images", type=int, default=1024, help="images per GPU for e2e_bytes")
+    ap.add_argument("--parity-images", type=int, default=32, help="images compared with the oracle port")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -187,6 +222,10 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    from lrf_b200.sharding import bind_host_to_gpu
+
+    # N > 1: pinned buffers and copy threads on the GPU's NUMA node (at N = 1 all cores stay available to the host legs)
+    affinity = bind_host_to_gpu(local_rank) if world > 1 else {"numa_node": None, "why": "single rank: not bound"}
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -261,6 +300,21 @@ def main():
     same = bool(torch.equal(h_out, plan.factors.cpu()))
     lib.lrfb_ctx_destroy(ctx)
 
+    # ---- plain concurrent H2D copy of the same bytes: the machine's ceiling for `e2e` (PCIe / host memory) ----------
+    d_probe = torch.empty_like(images)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        d_probe.copy_(h_in, non_blocking=True)
+    barrier()
+    h2d_s = (time.perf_counter() - t0) / 2
+    th = torch.tensor([h2d_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(th, op=dist.ReduceOp.MAX)
+    h2d_gbs_per_gpu = int(h_in.numel()) / float(th.item()) / 1e9
+    e2e_ceiling = mpix_step / float(th.item())  # Mpixel/s if the step were nothing but that copy
+    del d_probe
+
     # ---- roofline of the dominant kernel (BCD sweeps on the luma planes), timed alone with CUDA events --
     stream = torch.cuda.current_stream()
     xy, uy, vy = plan.view("x", 0), plan.view("u", 0), plan.view("v", 0)
@@ -299,38 +353,150 @@ def main():
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     fp32_peak = sms * 8 * 256 * it * 64 / (ff_ms / 1e3) / 1e12
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(tp):
+        tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
     if os.path.exists(tp):  # dram__bytes_read+write of this kernel from the committed ncu --set full capture
         with open(tp) as f:
             traffic = json.load(f)["bytes_per_image"] * B
+    achieved_tf = alg_flops / (bcd_ms / 1e3) / 1e12
     achieved_gbs = alg_bytes / (bcd_ms / 1e3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "bcd_tc_kernel<4,768,384>: all 10 BCD sweeps on the luma planes (lrfb_bcd)", "achieved": achieved_gbs,
-                "peak": peaks["hbm_gbs"], "peak_source": peak_src, "unit": "GB/s",
-                "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": traffic,
-                "ms_per_launch": bcd_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                "fp32": {"achieved_tflops": alg_flops / (bcd_ms / 1e3) / 1e12, "peak_tflops": fp32_peak,
-                         "frac": alg_flops / (bcd_ms / 1e3) / 1e12 / fp32_peak,
-                         "peak_source": "lrfb_ffma_probe measured in this run"}}
+    # The kernel keeps X on chip for all ten sweeps, so it is bound by arithmetic, not by HBM: the roofline is FP32.
+    roofline = {"bound": "fp32", "kernel": "bcd_tc_kernel<4,768,384>: all 10 BCD sweeps on the luma planes (lrfb_bcd)",
+                "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp32_peak,
+                "peak_source": "FP32 FFMA throughput measured in this run by lrfb_ffma_probe (MEASURED_PEAKS.json has no "
+                               "FP32 entry; nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.5)",
+                "traffic": traffic, "ms_per_launch": bcd_ms, "algorithmic_flops_per_launch": alg_flops,
+                "hbm": {"achieved_gbs": achieved_gbs, "peak_gbs": peaks["hbm_gbs"], "peak_source": peak_src,
+                        "frac": achieved_gbs / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": alg_bytes}}
     encode_fp32_frac = value * 1e6 / world * ALG_FLOP_PER_PIXEL / 1e12 / fp32_peak
+
+    def allmax(x):
+        t_ = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        return float(t_.item())
+
+    extras = {}
+    # ---- decode (lrf.qmf_decode's device part: int8 records -> uint8 RGB), HBM-bound -----------------------------
+    if not args.quick:
+        dec_buf = {}
+
+        def dec_step():
+            dec_buf["out"] = compression.decode_records(plan.factors, cfg)
+
+        dms = allmax(time_steps_ms(dec_step, 5, 3))
+        dec_bytes = B * (3 * H * W + lay.record_bytes)
+        extras["decode"] = {"value": mpix_step / (dms / 1e3), "unit": "Mpixel/s", "ms_per_step": dms,
+                            "workload": "qmf_decode device part on the %d records per GPU of the encode above" % B,
+                            "roofline": {"bound": "hbm", "achieved": dec_bytes / (dms / 1e3) / 1e9,
+                                         "peak": peaks["hbm_gbs"], "unit": "GB/s", "peak_source": peak_src,
+                                         "frac": dec_bytes / (dms / 1e3) / 1e9 / peaks["hbm_gbs"]}}
+        dec_buf.clear()
 
     # ---- quality / parity epilogue: per-image PSNR on device, bpp from host zlib on a sample; NCCL gather --
     dec = compression.decode_records(plan.factors, cfg)
     psnr = compression.psnr_batch(dec, images).float()
+    del dec
     n_s = min(B, POOL)
     host = plan.factors[:n_s].cpu().numpy()
     meta = compression._metadata(torch.uint8, "YCbCr", True, KW["bounds"], KW["patch_size"], lay)
     from lrf_b200 import packing
 
     t0 = time.perf_counter()
-    blobs = list(compression._pool().map(lambda i: packing.pack_qmf_record(host[i], lay, meta), range(n_s)))
+    blobs = compression.pack_records(host, cfg, lay, meta)
     pack_s = time.perf_counter() - t0
     bpp = torch.tensor([len(b) * 8 / (H * W) for b in blobs], dtype=torch.float32, device=dev)
     from lrf_b200.sharding import gather_stats
 
     stats = torch.stack([bpp, psnr[:n_s]], dim=1)
     stats = gather_stats(stats, n_s * world, rank, world).cpu()  # the only collective (NCCL all_gather)
+    psnr_host = psnr[:n_s].cpu()
+
+    # ---- end to end to `bytes`: host uint8 images -> H2D -> kernels -> D2H -> native zlib pool -> list[bytes] -----
+    if not args.quick:
+        n_b = min(B, args.bytes_images)
+        lrf_b200.qmf_encode_batch(h_in[:64], **KW)
+        barrier()
+        t0 = time.perf_counter()
+        out_b = lrf_b200.qmf_encode_batch(h_in[:n_b], **KW)
+        tb = allmax(time.perf_counter() - t0)
+        extras["e2e_bytes"] = {"value": world * n_b * H * W / 1e6 / tb, "unit": "Mpixel/s", "images_per_gpu": n_b,
+                               "call": "lrf_b200.qmf_encode_batch(host uint8 images) -> list[bytes] "
+                                       "(H2D, kernels, D2H, zlib level 9 on %d host threads, bytes objects)" % (os.cpu_count() or 1),
+                               "seconds": tb, "bytes_equal_sample_pack": out_b[:n_s] == blobs[:min(n_s, n_b)]}
+        del out_b
+
+    # free the 768x512 working set before the other shapes
+    del plan, images, xy, uy, vy, v0, s0y
+    torch.cuda.empty_cache()
+
+    # ---- configs[4]: CLIC-sized images (2048 x 1365), sharded like the headline: every rank its own batch ----------
+    if not args.quick:
+        Hc, Wc, Bc = 1365, 2048, args.clic_batch
+        from oracle import qmf_port as port
+
+        cpool = torch.stack([port.s_nat(1000 + i, Hc, Wc) for i in range(4)])
+        cimgs = cpool.to(dev)[((torch.arange(Bc) + rank * Bc) % 4).to(dev)].contiguous()
+        ccfg, clay = compression.resolve_plan(Hc, Wc, None, KW["quality"], "YCbCr", KW["scale_factor"], KW["patch_size"],
+                                              KW["bounds"], KW["num_iters"])
+        cplan = compression.EncodePlan(ccfg, clay, Bc, dev)
+        barrier()
+        cms = allmax(time_steps_ms(lambda: cplan.run(cimgs), 3, 3))
+        cmpix = world * Bc * Hc * Wc / 1e6
+        cfl = qmf_flops_per_image(clay, KW["num_iters"])
+        ctf = world * Bc * cfl / (cms / 1e3) / 1e12 / world
+        extras["clic"] = {"value": cmpix / (cms / 1e3), "unit": "Mpixel/s", "ms_per_step": cms,
+                          "workload": "configs[4] shape: %d synthetic 2048x1365 images per GPU (4 distinct, %.1f GB >> L2), "
+                                      "quality 7, 10 sweeps; M = (43776, 11008, 11008)" % (Bc, cimgs.numel() / 1e9),
+                          "roofline": {"bound": "fp32", "achieved": ctf, "peak": fp32_peak, "unit": "TFLOP/s",
+                                       "frac": ctf / fp32_peak, "flop_per_pixel": cfl / (Hc * Wc)}}
+        del cplan, cimgs
+        torch.cuda.empty_cache()
+
+    # ---- configs[2] (svd_encode) and configs[3] (ablation end points): N = 1 only ----------------------------------
+    if not args.quick and world == 1:
+        from oracle import qmf_port as port
+
+        Bs = args.side_batch
+        simgs = make_pool(8).to(dev)[(torch.arange(Bs) % 8).to(dev)].contiguous()
+        svd = {}
+        for q in (1.0, 7):
+            sms_ = time_steps_ms(lambda: lrf_b200.svd_encode_batch(simgs, quality=q, return_records=True), 2, 2)
+            svd["quality_%g" % q] = {"value": Bs * H * W / 1e6 / (sms_ / 1e3), "unit": "Mpixel/s", "ms_per_step": sms_,
+                                     "rank": max(round(192 * q / 100), 1)}
+        svd["workload"] = "configs[2]: svd_encode (RGB, 8x8 patches, M x 192 matrices) on %d 768x512 images" % Bs
+        extras["svd"] = svd
+        abl = {}
+        cases = {"iters_1": dict(num_iters=1), "iters_50": dict(num_iters=50), "patch_4x4": dict(patch_size=(4, 4)),
+                 "patch_16x16": dict(patch_size=(16, 16)), "bounds_-8_7": dict(bounds=(-8, 7)),
+                 "bounds_-128_127": dict(bounds=(-128, 127))}
+        for name, over in cases.items():
+            kw = dict(KW, **over)
+            acfg, alay = compression.resolve_plan(H, W, None, kw["quality"], "YCbCr", kw["scale_factor"], kw["patch_size"],
+                                                  kw["bounds"], kw["num_iters"])
+            ab = Bs if name.startswith(("iters", "bounds")) else max(8, Bs // 8)  # generic kernels for N != 64
+            aplan = compression.EncodePlan(acfg, alay, ab, dev)
+            ai = simgs[:ab].contiguous()
+            ams = time_steps_ms(lambda: aplan.run(ai), 2, 2)
+            afl = qmf_flops_per_image(alay, kw["num_iters"])
+            abl[name] = {"value": ab * H * W / 1e6 / (ams / 1e3), "unit": "Mpixel/s", "ms_per_step": ams, "batch": ab,
+                         "fp32_frac": ab * afl / (ams / 1e3) / 1e12 / fp32_peak}
+            del aplan
+        abl["workload"] = "configs[3] end points on 768x512 images (quality 7; everything else as the headline)"
+        extras["ablation"] = abl
+        del simgs
+        torch.cuda.empty_cache()
+
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
     if rank == 0:
+        quality = {"mean_bpp": float(stats[:, 0].mean()), "mean_psnr_db": float(stats[:, 1].mean()),
+                   "images": int(stats.shape[0])}
+        if not args.quick:
+            quality["vs_reference"] = parity_vs_reference(pool, blobs, psnr_host, host, lay, args.parity_images)
         line = {
             "metric": "QMF encode Mpixel/s (768x512, 10 iters)", "value": value, "unit": "Mpixel/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
@@ -339,21 +505,28 @@ def main():
             "config": {"workload": "configs[1]: batch of %d synthetic 768x512 RGB uint8 images per GPU, QMF "
                                    "quality 7, 8x8 patches, bounds (-16,15), int8, 10 sweeps" % B,
                        "batch_per_gpu": B, "distinct_images": POOL, "generator": "s_nat(seed=1000+i) SURVEY §8d",
-                       "l2": "inputs %.1f GB per GPU >> 126 MB L2, no flush needed" % (images.numel() / 1e9),
+                       "l2": "inputs %.1f GB per GPU >> 126 MB L2, no flush needed" % (B * 3 * H * W / 1e9),
                        "sharding": "images split across ranks, no data-path collective"},
             "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": int(h_in.numel()) * world,
                     "d2h_bytes_per_step": int(h_out.numel()) * world, "records_equal_device_path": same,
-                    "call": "lrfb_qmf_encode_host (C ABI, pinned host buffers)"},
+                    "call": "lrfb_qmf_encode_host (C ABI, pinned host buffers); stops at int8 factor records in host "
+                            "memory - see e2e_bytes for the run that ends in `bytes`",
+                    "host_affinity": affinity,
+                    "h2d_ceiling": {"value": e2e_ceiling, "unit": "Mpixel/s", "gbs_per_gpu": h2d_gbs_per_gpu,
+                                    "what": "the same pinned input copied to the device by plain concurrent "
+                                            "cudaMemcpyAsync on every rank, nothing else running",
+                                    "frac_of_ceiling": e2e_value / e2e_ceiling}},
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
             "roofline": roofline,
             "encode_fp32_frac": encode_fp32_frac,
             "encode_hbm_frac": value * 1e6 / world * ALG_BYTE_PER_PIXEL / 1e9 / peaks["hbm_gbs"],
-            "quality": {"mean_bpp": float(stats[:, 0].mean()), "mean_psnr_db": float(stats[:, 1].mean()),
-                        "images": int(stats.shape[0])},
+            "quality": quality,
             "host_pack": {"images": n_s, "seconds": pack_s, "threads": os.cpu_count(),
-                          "mpixel_per_s": n_s * H * W / 1e6 / pack_s},
+                          "mpixel_per_s": n_s * H * W / 1e6 / pack_s,
+                          "call": "lrfb_qmf_pack_host (native zlib-9 thread pool)"},
         }
+        line.update(extras)
         if not args.no_cpu_baseline and world == 1:  # N = 1 only: the other ranks must not wait on host work
             cores = os.cpu_count() or 1
             v, dt = cpu_reference_mpix(args.cpu_sample, cores)
@@ -361,9 +534,44 @@ def main():
                                     "sample": f"{args.cpu_sample} images of the workload in {dt:.1f} s "
                                               "(oracle port of the reference, zlib included)"}
         print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+
+
+def parity_vs_reference(pool, blobs, psnr_gpu, records, lay, n_img):
+    """north_star's parity figures on a sample of the benchmarked images: the oracle port (the reference's op sequence
+    on torch CPU) encodes the same images; compared with what the GPU path produced through the PUBLIC route (no test
+    hook): bytes, PSNR, factors, and a near-tie count for every image that differs."""
+    from oracle import exact
+    from oracle import qmf_port as port
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from backends import split_record
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    n = min(n_img, len(blobs), pool.shape[0])
+    dps, dbs, ident_b, ident_f, near_imgs, unexplained = [], [], 0, 0, 0, 0
+    for i in range(n):
+        img = pool[i]
+        blob_ref, ref, meta = port.qmf_encode(img, return_factors=True, **KW)
+        p_ref = port.psnr(img, port.qmf_decode(blob_ref))
+        dps.append(abs(float(psnr_gpu[i]) - p_ref))
+        dbs.append(abs(len(blobs[i]) - len(blob_ref)))
+        ident_b += blobs[i] == blob_ref
+        got = split_record(records[i], lay)
+        same = all(np.array_equal(g, r.numpy()) for g, r in zip(got, ref))
+        ident_f += same
+        if not same:
+            near = 0
+            for pl, (x, _, _) in enumerate(port.qmf_planes(img)):
+                u0, v0 = port.svd_init(x.unsqueeze(0), meta["rank"][pl])
+                near += exact.bcd(x.numpy(), u0.squeeze(0).numpy(), v0.squeeze(0).numpy(), KW["bounds"],
+                                  KW["num_iters"])[2].near_ties
+            near_imgs += near > 0
+            unexplained += near == 0
+    return {"images": n, "oracle": "oracle/qmf_port.py (torch CPU port of the reference) run in this process",
+            "max_abs_dpsnr_db": max(dps), "mean_abs_dbytes": float(np.mean(dbs)), "max_abs_dbytes": int(max(dbs)),
+            "frac_identical_bytes": ident_b / n, "frac_identical_factors": ident_f / n,
+            "route": "public path, nothing injected: the SVD init carries LAPACK's signs by the closed-form rule",
+            "differing_images_with_near_ties_1e-5": near_imgs, "differing_images_unexplained": unexplained}
 
 
 if __name__ == "__main__":

@@ -162,6 +162,24 @@ int32_t lrfb_qmf_encode_host(lrfb_ctx* ctx, const lrfb_qmf_config* cfg, int32_t 
                              int8_t* h_factors);
 int32_t lrfb_qmf_decode_host(lrfb_ctx* ctx, const lrfb_qmf_config* cfg, int32_t batch, const int8_t* h_factors,
                              uint8_t* h_images);
+/* Tuning: input bytes per pipeline chunk of the two host-buffer calls (default 256 MiB; the H2D copies of two chunks
+ * are in flight while the kernels consume a third). */
+int32_t lrfb_ctx_set_chunk_bytes(lrfb_ctx* ctx, int64_t bytes);
+
+/* Lossless packing on host threads — replaces the tail of lrf.qmf_encode (lrf/compression/qmf.py:288-292):
+ * encode_tensor / encode_matrix (zlib level 9 per factor column, lrf/compression/utils.py:354-390, :429-455),
+ * combine_bytes (:246-300) and the metadata header, byte for byte.  h_records: [batch][record_bytes] int8 records as
+ * lrfb_qmf_encode(_host) writes them; metadata_json: the utf-8 JSON header (identical for every image of a batch of
+ * one shape); image i's stream is written to h_out + i*out_stride (out_stride >= lrfb_qmf_pack_bound) and its length
+ * to out_sizes[i].  threads <= 0: one worker per hardware thread.  Pure host code (zlib), no device work. */
+int64_t lrfb_qmf_pack_bound(const lrfb_qmf_config* cfg, int64_t metadata_len);
+int32_t lrfb_qmf_pack_host(const lrfb_qmf_config* cfg, int32_t batch, const int8_t* h_records,
+                           const char* metadata_json, int64_t metadata_len, uint8_t* h_out, int64_t out_stride,
+                           int64_t* out_sizes, int32_t threads);
+
+/* Test hook: select a kernel variant process-wide.  Knobs: "decode_v1" (1 = per-row float decoder instead of the
+ * int8 dot-product one).  The shipped library reads no environment variables. */
+int32_t lrfb_debug_set(const char* knob, int32_t value);
 
 #ifdef __cplusplus
 }

@@ -82,6 +82,11 @@ PROTOTYPES = {
     "lrfb_ctx_destroy": (None, [C.c_void_p]),
     "lrfb_qmf_encode_host": (C.c_int32, [C.c_void_p, C.POINTER(QmfConfig), C.c_int32, C.c_void_p, C.c_void_p]),
     "lrfb_qmf_decode_host": (C.c_int32, [C.c_void_p, C.POINTER(QmfConfig), C.c_int32, C.c_void_p, C.c_void_p]),
+    "lrfb_ctx_set_chunk_bytes": (C.c_int32, [C.c_void_p, C.c_int64]),
+    "lrfb_qmf_pack_bound": (C.c_int64, [C.POINTER(QmfConfig), C.c_int64]),
+    "lrfb_qmf_pack_host": (C.c_int32, [C.POINTER(QmfConfig), C.c_int32, C.c_void_p, C.c_char_p, C.c_int64, C.c_void_p,
+                                       C.c_int64, C.c_void_p, C.c_int32]),
+    "lrfb_debug_set": (C.c_int32, [C.c_char_p, C.c_int32]),
 }
 
 

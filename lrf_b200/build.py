@@ -24,9 +24,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, os.path.join(CSRC, "lrfb_api.cu"), "-o", OUT]
+    cmd = [nvcc, *NVCC_FLAGS, os.path.join(CSRC, "lrfb_api.cu"), "-o", OUT, "-lz"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
+    if os.environ.get("LRFB_DEV"):  # development build: the library then honours its LRFB_* environment knobs
+        cmd.insert(1, "-DLRFB_DEV")
     subprocess.check_call(cmd)
     return OUT
 

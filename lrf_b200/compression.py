@@ -34,6 +34,26 @@ def _pool() -> ThreadPoolExecutor:
     return _POOL
 
 
+def pack_records(records: np.ndarray, cfg, lay, meta: dict, threads: int = 0) -> list[bytes]:
+    """int8 factor records (B, record_bytes) on the host + metadata → B encoded ``bytes``, on the native
+    thread pool of liblrfb.so (``lrfb_qmf_pack_host``: zlib level 9 per factor column and the reference's
+    byte framing, lrf/compression/utils.py:246-300, :354-390; identical output to packing.pack_qmf_record)."""
+    records = np.ascontiguousarray(records, np.int8)
+    B = records.shape[0]
+    assert records.ndim == 2 and records.shape[1] == lay.record_bytes
+    mj = packing.dict_to_bytes(meta)
+    lib = _cabi.lib()
+    stride = int(lib.lrfb_qmf_pack_bound(C.byref(cfg), len(mj)))
+    if stride <= 0:
+        raise _cabi.LrfbError("lrfb_qmf_pack_bound failed")
+    out = np.empty((B, stride), np.uint8)
+    sizes = np.zeros(B, np.int64)
+    rc = lib.lrfb_qmf_pack_host(C.byref(cfg), B, records.ctypes.data_as(C.c_void_p), mj, len(mj),
+                                out.ctypes.data_as(C.c_void_p), stride, sizes.ctypes.data_as(C.c_void_p), threads)
+    _cabi.check(rc, "lrfb_qmf_pack_host")
+    return [out[i, : sizes[i]].tobytes() for i in range(B)]
+
+
 def _require_cuda() -> None:
     if not torch.cuda.is_available():
         raise _cabi.LrfbError("lrf_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
@@ -183,7 +203,7 @@ def qmf_encode_batch(images: torch.Tensor, rank=None, quality=None, color_space:
         if return_records:
             return records, lay, meta
         host = records.cpu().numpy()
-    return list(_pool().map(lambda i: packing.pack_qmf_record(host[i], lay, meta), range(B)))
+    return pack_records(host, cfg, lay, meta)
 
 
 def qmf_encode(image: torch.Tensor, rank=None, quality=None, color_space: str = "YCbCr",

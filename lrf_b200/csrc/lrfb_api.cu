@@ -9,6 +9,12 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <atomic>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include <zlib.h>
 
 #include "bcd.cuh"
 #include "bcd_resident.cuh"
@@ -71,6 +77,17 @@ int num_sms() {
 #endif
 
 inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+// Environment knobs exist only in development builds (nvcc -DLRFB_DEV): the shipped library reads no environment.
+inline const char* dev_getenv(const char* name) {
+#ifdef LRFB_DEV
+  return getenv(name);
+#else
+  (void)name;
+  return nullptr;
+#endif
+}
+std::atomic<int> g_decode_v1{0};  // lrfb_debug_set("decode_v1", 1): per-row float decoder instead of the DP4A one
 
 struct Geometry {
   FrontParams fp;
@@ -200,7 +217,7 @@ template <int R>
 int launch_bcd_fast(const BcdBatch& b, cudaStream_t st) {
   static int variant = -1;  // dev knob: LRFB_BCD_VARIANT=0 (128 rows, 64 thr) | 1 (128, 128) | 2 (64, 64)
   if (variant < 0) {
-    const char* e = getenv("LRFB_BCD_VARIANT");
+    const char* e = dev_getenv("LRFB_BCD_VARIANT");
     variant = e ? atoi(e) : 1;
   }
   if (variant == 0) return launch_bcd_cfg<R, 128, 64>(b, st);
@@ -244,7 +261,7 @@ int launch_bcd_resident_cfg(const BcdBatch& b, cudaStream_t st) {
     max_clusters = std::max(1, num_sms() * (ROWS <= 384 ? 2 : 1) / csize);
   }
   cfg.gridDim = dim3((unsigned)(std::min(b.n_mat, max_clusters) * csize));
-  if (getenv("LRFB_DEBUG"))
+  if (dev_getenv("LRFB_DEBUG"))
     fprintf(stderr, "[lrfb] bcd_resident R=%d rows/cta=%d threads=%d cluster=%d max_active_clusters=%d grid=%u smem=%zu\n",
             R, ROWS, NT, csize, max_clusters, cfg.gridDim.x, smem);
   e = cudaLaunchKernelEx(&cfg, kern, b, csize, rows_per_cta);
@@ -267,7 +284,7 @@ bool make_x_tensor_map(const BcdBatch& b, CUtensorMap* out) {
     looked = true;
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult q;
-    if (!getenv("LRFB_NO_TMA") &&
+    if (!dev_getenv("LRFB_NO_TMA") &&
         cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
         q == cudaDriverEntryPointSuccess)
       encode = reinterpret_cast<EncodeFn>(fn);
@@ -304,7 +321,7 @@ int launch_bcd_tc_cfg(const BcdBatch& b, cudaStream_t st) {
   // 2 CTAs per SM only pay off when they belong to DIFFERENT clusters (CTAs of one cluster move in lock-step)
   attr[1].id = cudaLaunchAttributeClusterSchedulingPolicyPreference;
   attr[1].val.clusterSchedulingPolicyPreference = cudaClusterSchedulingPolicySpread;
-  static const int policy = getenv("LRFB_TC_POLICY") ? atoi(getenv("LRFB_TC_POLICY")) : 1;
+  static const int policy = dev_getenv("LRFB_TC_POLICY") ? atoi(dev_getenv("LRFB_TC_POLICY")) : 1;
   attr[1].val.clusterSchedulingPolicyPreference = (cudaClusterSchedulingPolicy)policy;
   cfg.blockDim = dim3(NT), cfg.dynamicSmemBytes = smem, cfg.stream = st, cfg.attrs = attr;
   cfg.numAttrs = (ROWS <= 384 && csize > 1) ? 2 : 1;
@@ -318,16 +335,16 @@ int launch_bcd_tc_cfg(const BcdBatch& b, cudaStream_t st) {
   // the occupancy calculation assumes one CTA per SM for any kernel that allocates tensor memory; two 384-row CTAs do
   // share an SM (tools/probes/occ_probe.cu).  Clusters that find no SM pair start late and find no work left.
   if (ROWS <= 384) max_clusters *= 2;
-  if (const char* ov = getenv("LRFB_TC_CLUSTERS")) max_clusters = std::max(1, atoi(ov) * 8 / csize);  // dev knob (per 8-CTA unit)
+  if (const char* ov = dev_getenv("LRFB_TC_CLUSTERS")) max_clusters = std::max(1, atoi(ov) * 8 / csize);  // dev knob (per 8-CTA unit)
   cfg.gridDim = dim3((unsigned)(std::min(b.n_mat, max_clusters) * csize));
-  if (getenv("LRFB_DEBUG")) {
+  if (dev_getenv("LRFB_DEBUG")) {
     int per_sm = -1;
     cudaFuncAttributes fa;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem);
     cudaFuncGetAttributes(&fa, kern);
     fprintf(stderr, "[lrfb] bcd_tc blocks/SM=%d regs=%d static_smem=%zu max_dyn=%d\n", per_sm, fa.numRegs, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes);
   }
-  if (getenv("LRFB_DEBUG"))
+  if (dev_getenv("LRFB_DEBUG"))
     fprintf(stderr, "[lrfb] bcd_tc R=%d rows/cta=%d threads=%d cluster=%d max_active_clusters=%d grid=%u smem=%zu\n",
             R, ROWS, NT, csize, max_clusters, cfg.gridDim.x, smem);
   CUtensorMap x_map;
@@ -340,7 +357,7 @@ int launch_bcd_tc_cfg(const BcdBatch& b, cudaStream_t st) {
 int tc_variant() {
   static int v = -1;  // dev knob: LRFB_TC_VARIANT=0 (768 rows x 384 threads, 1 CTA/SM) | 1 (384 x 192, 2 CTAs/SM)
   if (v < 0) {
-    const char* e = getenv("LRFB_TC_VARIANT");
+    const char* e = dev_getenv("LRFB_TC_VARIANT");
     v = e ? atoi(e) : 0;
   }
   return v;
@@ -354,7 +371,7 @@ int launch_bcd_tc(const BcdBatch& b, cudaStream_t st) {
 bool tc_enabled() {
   static int v = -1;  // dev knob: LRFB_BCD_TC=0 keeps the FFMA V-phase
   if (v < 0) {
-    const char* e = getenv("LRFB_BCD_TC");
+    const char* e = dev_getenv("LRFB_BCD_TC");
     v = e ? atoi(e) : 1;
   }
   return v != 0;
@@ -364,7 +381,7 @@ bool tc_enabled() {
 int resident_variant() {
   static int v = -1;  // dev knob: LRFB_RES_VARIANT=0 (768 rows, 1 CTA/SM) | 1 (384 rows, 2 CTAs/SM)
   if (v < 0) {
-    const char* e = getenv("LRFB_RES_VARIANT");
+    const char* e = dev_getenv("LRFB_RES_VARIANT");
     v = e ? atoi(e) : 0;
   }
   return v;
@@ -380,7 +397,7 @@ int launch_bcd_resident(const BcdBatch& b, cudaStream_t st) {
 bool resident_ok(int N, int R, int M) {
   static int enabled = -1;  // dev knob: LRFB_BCD_RESIDENT=0 forces the streaming kernel
   if (enabled < 0) {
-    const char* e = getenv("LRFB_BCD_RESIDENT");
+    const char* e = dev_getenv("LRFB_BCD_RESIDENT");
     enabled = e ? atoi(e) : 1;
   }
   if (!enabled || N != 64 || R > 4 || bmm_native(N, M, R)) return false;
@@ -466,7 +483,7 @@ int factorize_batch(const float* x, int n_mat, int M, int N, int R, float lo, fl
 #ifndef LRFB_SIM
       static int use_i8 = -1;  // dev knob: LRFB_GRAM_I8=0 keeps the FP64 (DMMA) Gram for uint8-range planes too
       if (use_i8 < 0) {
-        const char* ev = getenv("LRFB_GRAM_I8");
+        const char* ev = dev_getenv("LRFB_GRAM_I8");
         use_i8 = ev ? atoi(ev) : 1;
       }
       if (N == 64 && x_in_u8_range && use_i8 && (M + split - 1) / split <= 60000) {
@@ -504,7 +521,7 @@ int factorize_batch(const float* x, int n_mat, int M, int N, int R, float lo, fl
     // s0: f32 singular values stored behind the f64 ones
     static int eig_v3 = -1;  // dev knob: LRFB_EIG_V3=0 selects the one-warp shared-memory kernel
     if (eig_v3 < 0) {
-      const char* ev = getenv("LRFB_EIG_V3");
+      const char* ev = dev_getenv("LRFB_EIG_V3");
 #ifdef LRFB_SIM
       eig_v3 = ev ? atoi(ev) : 0;  // the 2-warp kernel is barrier-heavy: minutes per matrix on the CPU shim
 #else
@@ -535,27 +552,45 @@ int factorize_batch(const float* x, int n_mat, int M, int N, int R, float lo, fl
 
 #ifndef LRFB_SIM
 // Helper stream per device so the chroma sweeps can fill the SMs the luma clusters leave idle.
+// One set per device, shared by every caller: `mu` is held from the first record to the last wait of a call (a call only
+// ENQUEUES work, so the critical section is short), which keeps two host threads from interleaving their
+// cudaEventRecord / cudaStreamWaitEvent pairs on the shared events.  A partially initialised set is never handed out.
 struct SideStream {
+  std::mutex mu;
+  bool ready = false, failed = false;
   cudaStream_t stream = nullptr, stream2 = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr, init2 = nullptr;
 };
-SideStream* side_stream() {
+SideStream* side_stream() {  // returns with s->mu LOCKED (or nullptr)
   static SideStream table[64];
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
   SideStream& s = table[dev];
-  if (!s.stream) {
+  s.mu.lock();
+  if (!s.ready && !s.failed) {
     // lowest priority: luma-chain blocks (caller's stream) are scheduled first, chroma fills what is left
     int least = 0, greatest = 0;
     cudaDeviceGetStreamPriorityRange(&least, &greatest);
-    if (cudaStreamCreateWithPriority(&s.stream, cudaStreamNonBlocking, least) != cudaSuccess) return nullptr;
-    if (cudaStreamCreateWithPriority(&s.stream2, cudaStreamNonBlocking, least) != cudaSuccess) return nullptr;
-    cudaEventCreateWithFlags(&s.init2, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming);
+    bool ok = cudaStreamCreateWithPriority(&s.stream, cudaStreamNonBlocking, least) == cudaSuccess &&
+              cudaStreamCreateWithPriority(&s.stream2, cudaStreamNonBlocking, least) == cudaSuccess &&
+              cudaEventCreateWithFlags(&s.init2, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) cudaGetLastError();
+    s.ready = ok, s.failed = !ok;
+  }
+  if (!s.ready) {
+    s.mu.unlock();
+    return nullptr;
   }
   return &s;
 }
+struct SideUnlock {  // releases the set on every exit path of lrfb_qmf_encode
+  SideStream* s;
+  ~SideUnlock() {
+    if (s) s->mu.unlock();
+  }
+};
 #endif
 
 int64_t encode_scratch_bytes(const Geometry& g, int batch) {
@@ -708,12 +743,13 @@ LRFB_EXPORT int32_t lrfb_qmf_encode(const lrfb_qmf_config* cfg, int32_t batch, c
   // overlaps the DMMA-bound Gram of another and the luma chain is the only critical path.
   bool overlap = false;
 #ifndef LRFB_SIM
-  overlap = L.n_planes == 3 && !(dbg && dbg->stop_after) && cfg->num_iters > 0 && !getenv("LRFB_NO_OVERLAP");
+  overlap = L.n_planes == 3 && !(dbg && dbg->stop_after) && cfg->num_iters > 0 && !dev_getenv("LRFB_NO_OVERLAP");
   for (int pl = 0; pl < L.n_planes && overlap; ++pl) overlap = resident_ok(L.cols, L.rank[pl], L.rows[pl]);
   SideStream* side = overlap ? side_stream() : nullptr;
+  SideUnlock side_guard{side};
   overlap = overlap && side;
   if (overlap) {
-    bool chains = !getenv("LRFB_NO_CHAIN_OVERLAP");
+    bool chains = !dev_getenv("LRFB_NO_CHAIN_OVERLAP");
     for (int pl = 0; pl < 3 && chains; ++pl) chains = FactorWs::gram_split(batch, L.rows[pl]) == 1;
     if (chains) {
       // Three initialisation chains (Gram + eigen-solver: the latter latency-bound) run side by side; then the luma
@@ -730,7 +766,7 @@ LRFB_EXPORT int32_t lrfb_qmf_encode(const lrfb_qmf_config* cfg, int32_t batch, c
         cudaEventRecord(side->fork, side->stream);
       }
       cudaStreamWaitEvent(side->stream2, side->fork, 0);
-      static const bool timeline = getenv("LRFB_TIMELINE") != nullptr;  // dev aid: when does each chain finish?
+      static const bool timeline = dev_getenv("LRFB_TIMELINE") != nullptr;  // dev aid: when does each chain finish?
       cudaEvent_t ev[8] = {};
       if (timeline) {
         for (auto& e : ev) cudaEventCreate(&e);
@@ -864,7 +900,7 @@ LRFB_EXPORT int32_t lrfb_qmf_decode(const lrfb_qmf_config* cfg, int32_t batch, c
     long long items = hw / 8;
 #ifndef LRFB_SIM
     if (fused8_geometry(cfg, g, d_images) && g.lay.rank[0] <= 4 && g.lay.rank[1] <= 4 && g.lay.rank[2] <= 4 &&
-        !getenv("LRFB_DECODE_V1")) {
+        !g_decode_v1.load(std::memory_order_relaxed)) {
       dim3 grid2((unsigned)std::min<long long>((items / 2 + 255) / 256, 4096), std::min(batch, 65535));
       LRFB_LAUNCH(qmf_decode8x2_kernel, grid2, dim3(256), 0, (cudaStream_t)(uintptr_t)stream, d_factors, d_images, P);
       return check_launch("qmf_decode8x2_kernel");
@@ -969,16 +1005,19 @@ LRFB_EXPORT int32_t lrfb_sse_u8(const uint8_t* d_a, const uint8_t* d_b, int64_t 
 
 // ---- host-buffer path ----------------------------------------------------------------------------
 
+constexpr int kHostSlots = 3;  // input chunks in flight: one being consumed by the kernels, two on the wire
 struct lrfb_ctx {
   int device;
   cudaStream_t stream;   // compute + D2H
   cudaStream_t copy;     // H2D
-  void* d_in;            // two chunk-sized input buffers back to back
-  void* d_out;
+  void* d_in;            // kHostSlots chunk-sized input buffers back to back
+  void* d_out;           // two chunk-sized record buffers (the D2H of chunk i overlaps the kernels of chunk i+1)
   void* d_ws;
   size_t in_cap, out_cap, ws_cap;
+  size_t chunk_bytes;    // input bytes per pipeline chunk
 #ifndef LRFB_SIM
-  cudaEvent_t landed[2], consumed[2];
+  cudaStream_t back;     // D2H
+  cudaEvent_t landed[kHostSlots], consumed[kHostSlots], encoded[2], drained[2];
 #endif
 };
 
@@ -1000,6 +1039,7 @@ LRFB_EXPORT int32_t lrfb_ctx_create(int32_t device, lrfb_ctx** out) {
   *out = new lrfb_ctx();
   memset(*out, 0, sizeof(lrfb_ctx));
   (*out)->device = device;
+  (*out)->chunk_bytes = (size_t)256 << 20;
   return 0;
 }
 LRFB_EXPORT void lrfb_ctx_destroy(lrfb_ctx* c) {
@@ -1038,11 +1078,17 @@ LRFB_EXPORT int32_t lrfb_ctx_create(int32_t device, lrfb_ctx** out) {
   lrfb_ctx* c = new lrfb_ctx();
   memset(c, 0, sizeof(*c));
   c->device = device;
+  c->chunk_bytes = (size_t)256 << 20;
   e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking);
-  for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->back, cudaStreamNonBlocking);
+  for (int i = 0; i < kHostSlots && e == cudaSuccess; ++i) {
     e = cudaEventCreateWithFlags(&c->landed[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->consumed[i], cudaEventDisableTiming);
+  }
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+    e = cudaEventCreateWithFlags(&c->encoded[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->drained[i], cudaEventDisableTiming);
   }
   if (e != cudaSuccess) {
     delete c;
@@ -1057,55 +1103,78 @@ LRFB_EXPORT void lrfb_ctx_destroy(lrfb_ctx* c) {
   if (c->d_in) cudaFree(c->d_in);
   if (c->d_out) cudaFree(c->d_out);
   if (c->d_ws) cudaFree(c->d_ws);
-  for (int i = 0; i < 2; ++i) cudaEventDestroy(c->landed[i]), cudaEventDestroy(c->consumed[i]);
+  for (int i = 0; i < kHostSlots; ++i) cudaEventDestroy(c->landed[i]), cudaEventDestroy(c->consumed[i]);
+  for (int i = 0; i < 2; ++i) cudaEventDestroy(c->encoded[i]), cudaEventDestroy(c->drained[i]);
+  cudaStreamDestroy(c->back);
   cudaStreamDestroy(c->copy);
   cudaStreamDestroy(c->stream);
   delete c;
 }
 #endif
 
-// Chunked, double-buffered pipeline: the H2D copy of chunk i+1 (copy stream) overlaps the kernels of chunk i
-// (compute stream); the int8 records of a chunk go back on the compute stream as soon as it finishes.  The
-// workspace is sized for one chunk, so host batches larger than device memory would allow still encode.
+LRFB_EXPORT int32_t lrfb_ctx_set_chunk_bytes(lrfb_ctx* c, int64_t bytes) {
+  if (!c || bytes <= 0) return fail(LRFB_E_ARG, "bad arguments");
+  c->chunk_bytes = (size_t)bytes;
+  return 0;
+}
+
+// Chunked pipeline over three streams: H2D of chunks i+1, i+2 (copy stream) | kernels of chunk i (compute stream) |
+// D2H of the int8 records of chunk i-1 (back stream).  The workspace is sized for one chunk, so host batches larger
+// than device memory would allow still encode.
 LRFB_EXPORT int32_t lrfb_qmf_encode_host(lrfb_ctx* c, const lrfb_qmf_config* cfg, int32_t batch,
                                          const void* h_images, int8_t* h_factors) {
   if (!c || !h_images || !h_factors || batch <= 0) return fail(LRFB_E_ARG, "bad arguments");
-  lrfb_qmf_workspace_map m;
+  lrfb_qmf_workspace_map m, mt;
   lrfb_qmf_layout L;
   int rc;
   if ((rc = lrfb_qmf_layout_query(cfg, &L))) return rc;
   const size_t img_bytes = (size_t)3 * cfg->height * cfg->width * (cfg->input_dtype == LRFB_U8 ? 1 : 4);
-  // ~0.3 GB of input per chunk: long enough to hide launch latency, short enough to overlap well
-  int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)batch, ((size_t)320 << 20) / std::max<size_t>(img_bytes, 1)));
+  const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)batch, c->chunk_bytes / std::max<size_t>(img_bytes, 1)));
+  // the scratch need is not monotonic in the batch (the Gram row split grows as the batch shrinks): size the workspace
+  // for the full chunk AND for the ragged tail
   if ((rc = lrfb_qmf_workspace_query(cfg, chunk, &m))) return rc;
+  int64_t ws_need = m.total_bytes;
+  if (batch % chunk) {
+    if ((rc = lrfb_qmf_workspace_query(cfg, batch % chunk, &mt))) return rc;
+    ws_need = std::max(ws_need, mt.total_bytes);
+  }
 #ifndef LRFB_SIM
   cudaSetDevice(c->device);
 #endif
-  if ((rc = grow(&c->d_in, &c->in_cap, 2 * (size_t)chunk * img_bytes))) return rc;
-  if ((rc = grow(&c->d_out, &c->out_cap, (size_t)chunk * L.record_bytes))) return rc;
-  if ((rc = grow(&c->d_ws, &c->ws_cap, (size_t)m.total_bytes))) return rc;
+  if ((rc = grow(&c->d_in, &c->in_cap, (size_t)kHostSlots * chunk * img_bytes))) return rc;
+  if ((rc = grow(&c->d_out, &c->out_cap, (size_t)2 * chunk * L.record_bytes))) return rc;
+  if ((rc = grow(&c->d_ws, &c->ws_cap, (size_t)ws_need))) return rc;
   const unsigned char* src = reinterpret_cast<const unsigned char*>(h_images);
   int idx = 0;
   for (int i0 = 0; i0 < batch; i0 += chunk, ++idx) {
     const int n = std::min(chunk, batch - i0);
-    const int slot = idx & 1;
+    const int slot = idx % kHostSlots, oslot = idx & 1;
     unsigned char* d_in = reinterpret_cast<unsigned char*>(c->d_in) + (size_t)slot * chunk * img_bytes;
+    int8_t* d_out = reinterpret_cast<int8_t*>(c->d_out) + (size_t)oslot * chunk * L.record_bytes;
 #ifndef LRFB_SIM
-    if (idx >= 2) cudaStreamWaitEvent(c->copy, c->consumed[slot], 0);  // kernels of chunk idx-2 are done with it
+    if (idx >= kHostSlots) cudaStreamWaitEvent(c->copy, c->consumed[slot], 0);  // kernels of chunk idx-3 are done with it
     if ((rc = h2d(d_in, src + (size_t)i0 * img_bytes, (size_t)n * img_bytes, c->copy))) return rc;
     cudaEventRecord(c->landed[slot], c->copy);
     cudaStreamWaitEvent(c->stream, c->landed[slot], 0);
+    if (idx >= 2) cudaStreamWaitEvent(c->stream, c->drained[oslot], 0);  // records of chunk idx-2 have left d_out
 #else
     if ((rc = h2d(d_in, src + (size_t)i0 * img_bytes, (size_t)n * img_bytes, c->stream))) return rc;
 #endif
-    if ((rc = lrfb_qmf_encode(cfg, n, d_in, (int8_t*)c->d_out, c->d_ws, m.total_bytes, nullptr,
-                              (void*)(uintptr_t)c->stream)))
+    if ((rc = lrfb_qmf_encode(cfg, n, d_in, d_out, c->d_ws, (int64_t)c->ws_cap, nullptr, (void*)(uintptr_t)c->stream)))
       return rc;
 #ifndef LRFB_SIM
     cudaEventRecord(c->consumed[slot], c->stream);
+    cudaEventRecord(c->encoded[oslot], c->stream);
+    cudaStreamWaitEvent(c->back, c->encoded[oslot], 0);
+    if ((rc = d2h(h_factors + (size_t)i0 * L.record_bytes, d_out, (size_t)n * L.record_bytes, c->back))) return rc;
+    cudaEventRecord(c->drained[oslot], c->back);
+#else
+    if ((rc = d2h(h_factors + (size_t)i0 * L.record_bytes, d_out, (size_t)n * L.record_bytes, c->stream))) return rc;
 #endif
-    if ((rc = d2h(h_factors + (size_t)i0 * L.record_bytes, c->d_out, (size_t)n * L.record_bytes, c->stream))) return rc;
   }
+#ifndef LRFB_SIM
+  if ((rc = sync_stream(c->back))) return rc;
+#endif
   return sync_stream(c->stream);
 }
 
@@ -1118,13 +1187,138 @@ LRFB_EXPORT int32_t lrfb_qmf_decode_host(lrfb_ctx* c, const lrfb_qmf_config* cfg
 #ifndef LRFB_SIM
   cudaSetDevice(c->device);
 #endif
-  size_t img_bytes = (size_t)batch * 3 * cfg->height * cfg->width;
-  size_t fac_bytes = (size_t)batch * L.record_bytes;
-  if ((rc = grow(&c->d_in, &c->in_cap, fac_bytes))) return rc;
-  if ((rc = grow(&c->d_out, &c->out_cap, img_bytes))) return rc;
-  if ((rc = h2d(c->d_in, h_factors, fac_bytes, c->stream))) return rc;
-  if ((rc = lrfb_qmf_decode(cfg, batch, (const int8_t*)c->d_in, (uint8_t*)c->d_out, (void*)(uintptr_t)c->stream)))
-    return rc;
-  if ((rc = d2h(h_images, c->d_out, img_bytes, c->stream))) return rc;
+  const size_t img_bytes = (size_t)3 * cfg->height * cfg->width;
+  const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)batch, c->chunk_bytes / std::max<size_t>(img_bytes, 1)));
+  // d_in doubles as the record buffer (whole batch: records are ~40x smaller than images), d_out holds two image chunks
+  if ((rc = grow(&c->d_in, &c->in_cap, (size_t)batch * L.record_bytes))) return rc;
+  if ((rc = grow(&c->d_out, &c->out_cap, (size_t)2 * chunk * img_bytes))) return rc;
+  if ((rc = h2d(c->d_in, h_factors, (size_t)batch * L.record_bytes, c->stream))) return rc;
+  int idx = 0;
+  for (int i0 = 0; i0 < batch; i0 += chunk, ++idx) {
+    const int n = std::min(chunk, batch - i0);
+    const int oslot = idx & 1;
+    uint8_t* d_img = reinterpret_cast<uint8_t*>(c->d_out) + (size_t)oslot * chunk * img_bytes;
+#ifndef LRFB_SIM
+    if (idx >= 2) cudaStreamWaitEvent(c->stream, c->drained[oslot], 0);
+#endif
+    if ((rc = lrfb_qmf_decode(cfg, n, reinterpret_cast<const int8_t*>(c->d_in) + (size_t)i0 * L.record_bytes, d_img,
+                              (void*)(uintptr_t)c->stream)))
+      return rc;
+#ifndef LRFB_SIM
+    cudaEventRecord(c->encoded[oslot], c->stream);
+    cudaStreamWaitEvent(c->back, c->encoded[oslot], 0);
+    if ((rc = d2h(h_images + (size_t)i0 * img_bytes, d_img, (size_t)n * img_bytes, c->back))) return rc;
+    cudaEventRecord(c->drained[oslot], c->back);
+#else
+    if ((rc = d2h(h_images + (size_t)i0 * img_bytes, d_img, (size_t)n * img_bytes, c->stream))) return rc;
+#endif
+  }
+#ifndef LRFB_SIM
+  if ((rc = sync_stream(c->back))) return rc;
+#endif
   return sync_stream(c->stream);
+}
+
+// ---- lossless packing on host threads (the reference's encode_tensor / combine_bytes, byte for byte) ----------------
+
+namespace {
+typedef std::vector<unsigned char> Bytes;
+void put_be32(Bytes& o, size_t v) {
+  o.push_back((unsigned char)(v >> 24)), o.push_back((unsigned char)(v >> 16));
+  o.push_back((unsigned char)(v >> 8)), o.push_back((unsigned char)v);
+}
+// combine_bytes(parts) = left fold of combine(a, b) = BE32(len a) | a | b  (lrf/compression/utils.py:246-300): the
+// result is the k-1 nested length prefixes (outermost first) followed by the parts themselves
+void combine_into(Bytes& out, const std::vector<const Bytes*>& parts) {
+  std::vector<size_t> acc(parts.size());
+  size_t run = parts[0]->size();
+  acc[0] = run;
+  for (size_t i = 1; i < parts.size(); ++i) acc[i] = run = 4 + run + parts[i]->size();
+  for (size_t i = parts.size() - 1; i >= 1; --i) put_be32(out, acc[i - 1]);
+  for (const Bytes* p : parts) out.insert(out.end(), p->begin(), p->end());
+}
+// encode_matrix (lrf/compression/utils.py:354-390) of one fiber-major factor: R columns of `rows` int8 each
+int encode_fibers(Bytes& out, const int8_t* fibers, int R, int rows, const char* dtype_name, std::vector<Bytes>& cols) {
+  cols.resize(R);
+  for (int r = 0; r < R; ++r) {
+    uLongf cap = compressBound((uLong)rows);
+    cols[r].resize(cap);
+    int zr = compress2(cols[r].data(), &cap, reinterpret_cast<const Bytef*>(fibers) + (size_t)r * rows, (uLong)rows, 9);
+    if (zr != Z_OK) return zr;
+    cols[r].resize(cap);
+  }
+  char hdr[96];
+  int n = snprintf(hdr, sizeof(hdr), "{\"num_fibers\": %d, \"mode\": \"col\", \"dtype\": \"%s\"}", R, dtype_name);
+  Bytes meta(hdr, hdr + n), body;
+  std::vector<const Bytes*> cp;
+  for (auto& cb : cols) cp.push_back(&cb);
+  combine_into(body, cp);
+  combine_into(out, {&meta, &body});
+  return 0;
+}
+}  // namespace
+
+LRFB_EXPORT int64_t lrfb_qmf_pack_bound(const lrfb_qmf_config* cfg, int64_t metadata_len) {
+  lrfb_qmf_layout L;
+  if (lrfb_qmf_layout_query(cfg, &L) || metadata_len < 0) return -1;
+  int64_t b = 8 + metadata_len;
+  for (int pl = 0; pl < L.n_planes; ++pl)
+    b += 2 * (128 + 8) + (int64_t)L.rank[pl] * (8 + (int64_t)compressBound((uLong)L.rows[pl]) + (int64_t)compressBound((uLong)L.cols));
+  return b;
+}
+
+LRFB_EXPORT int32_t lrfb_qmf_pack_host(const lrfb_qmf_config* cfg, int32_t batch, const int8_t* h_records,
+                                       const char* metadata_json, int64_t metadata_len, uint8_t* h_out,
+                                       int64_t out_stride, int64_t* out_sizes, int32_t threads) {
+  if (!h_records || !metadata_json || !h_out || !out_sizes || batch <= 0 || metadata_len <= 0)
+    return fail(LRFB_E_ARG, "bad arguments");
+  lrfb_qmf_layout L;
+  int rc = lrfb_qmf_layout_query(cfg, &L);
+  if (rc) return rc;
+  if (out_stride < lrfb_qmf_pack_bound(cfg, metadata_len)) return fail(LRFB_E_WORKSPACE, "out_stride below lrfb_qmf_pack_bound");
+  int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+  nt = std::max(1, std::min(nt, (int)batch));
+  std::atomic<int> next{0}, err{0};
+  auto work = [&]() {
+    std::vector<Bytes> cols;
+    Bytes meta(metadata_json, metadata_json + metadata_len), body, img;
+    std::vector<Bytes> enc(2 * L.n_planes);
+    for (;;) {
+      const int i = next.fetch_add(1);
+      if (i >= batch || err.load()) break;
+      const int8_t* rec = h_records + (size_t)i * L.record_bytes;
+      for (int pl = 0; pl < L.n_planes; ++pl) {
+        enc[2 * pl].clear(), enc[2 * pl + 1].clear();
+        int z = encode_fibers(enc[2 * pl], rec + L.u_offset[pl], L.rank[pl], L.rows[pl], "int8", cols);
+        if (!z) z = encode_fibers(enc[2 * pl + 1], rec + L.v_offset[pl], L.rank[pl], L.cols, "int8", cols);
+        if (z) err.store(z);
+      }
+      body.clear(), img.clear();
+      std::vector<const Bytes*> ep;
+      for (auto& e : enc) ep.push_back(&e);
+      combine_into(body, ep);
+      combine_into(img, {&meta, &body});
+      if ((int64_t)img.size() > out_stride) {
+        err.store(-100);
+        break;
+      }
+      memcpy(h_out + (size_t)i * out_stride, img.data(), img.size());
+      out_sizes[i] = (int64_t)img.size();
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < nt; ++t) pool.emplace_back(work);
+  work();
+  for (auto& t : pool) t.join();
+  if (err.load()) return fail(LRFB_E_UNSUPPORTED, "zlib / packing failed (%d)", err.load());
+  return 0;
+}
+
+LRFB_EXPORT int32_t lrfb_debug_set(const char* knob, int32_t value) {
+  if (!knob) return fail(LRFB_E_ARG, "knob is null");
+  if (!strcmp(knob, "decode_v1")) {
+    g_decode_v1.store(value);
+    return 0;
+  }
+  return fail(LRFB_E_ARG, "unknown knob '%s'", knob);
 }

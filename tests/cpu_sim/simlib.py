@@ -28,7 +28,7 @@ def build() -> str:
     subprocess.check_call([
         "g++", "-std=c++20", "-O2", "-pthread", "-DLRFB_SIM", "-ffp-contract=off", "-fvisibility=hidden",
         "-fPIC", "-shared", "-I", _HERE, "-I", _CSRC, "-x", "c++", os.path.join(_CSRC, "lrfb_api.cu"),
-        "-o", _SO,
+        "-o", _SO, "-lz",
     ])
     return _SO
 

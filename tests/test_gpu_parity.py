@@ -69,6 +69,52 @@ def test_own_svd_init_sign_aligned_matches_reference(gpu, manifest, name):
         assert sum(diffs) == 0, diffs
 
 
+# fixtures whose planes are all "tall" 8x8-patch matrices (M >= 1.5 N, R <= 4): the product path must carry LAPACK's signs
+TALL = ["snat9_128x192_q7", "snat1000_512x768_q7", "snat1001_512x768_q7", "snat1002_512x768_q7",
+        "snat1003_512x768_q7", "kodim01_q7", "snat1000_1365x2048_q7", "snat1000_256x384_b8", "snat1000_256x384_b128",
+        "snat1000_256x384_it1", "snat1000_256x384_it2", "snat1000_256x384_it5", "snat1000_256x384_it20",
+        "snat1000_256x384_rank", "snat1000_256x384_p4"]
+
+
+@pytest.mark.parametrize("name", TALL)
+def test_product_path_carries_lapack_signs(gpu, manifest, name):
+    """No test hook: the SVD init of the product path has LAPACK's column signs (closed-form rule in eig.cuh)."""
+    pc.check_product_signs(gpu, manifest, name)
+
+
+@pytest.mark.parametrize("name", ["snat9_128x192_q7", "snat1000_512x768_q7", "snat1001_512x768_q7",
+                                  "snat1002_512x768_q7", "snat1003_512x768_q7", "kodim01_q7"])
+def test_public_api_bytes_identical_to_reference(manifest, name):
+    """north_star "bpp identical": lrf_b200.qmf_encode(image) == the bytes the unmodified reference produced, through
+    the public API with nothing injected (front end, SVD init incl. LAPACK's signs, sweeps, packing)."""
+    import lrf_b200
+
+    e = manifest["cases"][name]
+    img = golden_image(e["image"])
+    blob = lrf_b200.qmf_encode(img, **golden_kwargs(e))
+    assert hashlib.sha256(blob).hexdigest() == e["sha256"], (len(blob), e["bytes"])
+
+
+@pytest.mark.parametrize("name", ["snat1000_1365x2048_q7", "snat1000_256x384_b8", "snat1000_256x384_b128",
+                                  "snat1000_256x384_it1", "snat1000_256x384_it2", "snat1000_256x384_it5",
+                                  "snat1000_256x384_it20", "snat1000_256x384_rank", "snat1000_256x384_p4",
+                                  "snat1000_256x384_p16", "snat1000_128x192_rgb", "siid2000_512x768_q7"])
+def test_public_api_within_north_star_tolerances(manifest, name):
+    """Every other fixture through the public API: PSNR within 0.01 dB and bytes within 1 % of the reference
+    (identical unless a near-tie or, for N != 64 / R > 4 / noise images, an un-modelled LAPACK sign intervenes)."""
+    import lrf_b200
+
+    e = manifest["cases"][name]
+    img = golden_image(e["image"])
+    blob = lrf_b200.qmf_encode(img, **golden_kwargs(e))
+    psnr = port.psnr(img, lrf_b200.qmf_decode(blob))
+    tol_db = 0.01 if not name.startswith("siid") else 0.02   # S-iid: near-degenerate spectrum, SURVEY §8d
+    assert abs(psnr - e["psnr"]) <= tol_db, (psnr, e["psnr"])
+    assert abs(len(blob) - e["bytes"]) <= 0.01 * e["bytes"], (len(blob), e["bytes"])
+    print(f"\n[public api] {name}: identical={hashlib.sha256(blob).hexdigest() == e['sha256']} "
+          f"bytes {len(blob)} vs {e['bytes']}, psnr {psnr:.4f} vs {e['psnr']:.4f}")
+
+
 @pytest.mark.parametrize("name", ["kodim01_q7", "snat1000_512x768_q7", "snat1000_1365x2048_q7",
                                   "snat7_45x70_q7", "snat1000_256x384_p4", "snat1000_256x384_p16",
                                   "snat1000_128x192_rgb"])
@@ -88,9 +134,8 @@ def test_public_api_roundtrip_kodim(manifest):
     dec_ref = port.qmf_decode(blob)  # the reference decoder reads our stream
     assert torch.equal(dec_gpu, dec_ref)
     psnr = port.psnr(img, dec_gpu)
-    # signs of SVD components >= 2 are not aligned here, so bytes/PSNR may move by the H1 amounts
-    assert abs(psnr - e["psnr"]) < 0.05, (psnr, e["psnr"])
-    assert abs(len(blob) - e["bytes"]) <= 0.02 * e["bytes"]
+    assert abs(psnr - e["psnr"]) <= 0.01, (psnr, e["psnr"])
+    assert abs(len(blob) - e["bytes"]) <= 0.01 * e["bytes"]
     # and our decoder reads the reference's stream, bit-exactly
     assert hashlib.sha256(lrf_b200.qmf_decode(golden_bytes("kodim01_q7")).numpy().tobytes()).hexdigest() == \
         e["decoded_sha256"]
@@ -149,7 +194,7 @@ def test_full_size_batch_properties(gpu):
     psnr = lrf_b200.psnr_batch(dec, imgs.cuda()).cpu()
     for i in range(4):
         ref = port.psnr(base[i], port.qmf_decode(port.qmf_encode(base[i], **README_KW)))
-        assert abs(float(psnr[i]) - ref) < 0.05, (i, float(psnr[i]), ref)
+        assert abs(float(psnr[i]) - ref) <= 0.01, (i, float(psnr[i]), ref)
 
 
 def test_qmf_class_decompose_matches_oracle(gpu):
@@ -235,7 +280,7 @@ def test_eval_compression_mirror(manifest):
     out = lrf_b200.eval_compression(img, lrf_b200.qmf_encode, lrf_b200.qmf_decode, **README_KW)
     assert set(out) == {"compression ratio", "bit rate (bpp)", "PSNR (dB)", "SSIM", "encoding time (ms)",
                         "decoding time (ms)"}
-    assert abs(out["PSNR (dB)"] - e["psnr"]) < 0.05 and abs(out["bit rate (bpp)"] - e["bpp"]) < 0.02 * e["bpp"]
+    assert abs(out["PSNR (dB)"] - e["psnr"]) <= 0.01 and abs(out["bit rate (bpp)"] - e["bpp"]) <= 0.01 * e["bpp"]
     b = lrf_b200.eval_qmf_batch(torch.stack([img, img]), **README_KW)
     assert abs(float(b["PSNR (dB)"][1]) - out["PSNR (dB)"]) < 1e-4
 
@@ -257,10 +302,86 @@ def test_decode_kernels_agree(monkeypatch, shape, rank):
     cfg, _ = compression.resolve_plan(H, W, kw.get("rank"), kw.get("quality"), "YCbCr", (0.5, 0.5), (8, 8), (-16, 15), 10)
     g = torch.Generator().manual_seed(5)
     noise = torch.randint(-128, 128, rec.shape, generator=g, dtype=torch.int8).cuda()  # any int8 factors must agree
+    from lrf_b200 import _cabi
+
     for records in (rec, noise):
-        monkeypatch.delenv("LRFB_DECODE_V1", raising=False)
-        fast = compression.decode_records(records, cfg)
-        monkeypatch.setenv("LRFB_DECODE_V1", "1")
-        slow = compression.decode_records(records, cfg)
-        monkeypatch.delenv("LRFB_DECODE_V1", raising=False)
+        try:
+            fast = compression.decode_records(records, cfg)
+            _cabi.check(_cabi.lib().lrfb_debug_set(b"decode_v1", 1), "lrfb_debug_set")
+            slow = compression.decode_records(records, cfg)
+        finally:
+            _cabi.lib().lrfb_debug_set(b"decode_v1", 0)
         assert torch.equal(fast, slow)
+
+
+@pytest.mark.parametrize("shape,batch,chunk_images", [((128, 192), 37, 8), ((512, 768), 21, 8), ((96, 160), 5, 100)])
+def test_host_buffer_calls_match_device_path(shape, batch, chunk_images):
+    """lrfb_qmf_encode_host / lrfb_qmf_decode_host (pinned host buffers, chunked three-stream pipeline) with a batch that
+    is not a multiple of the chunk: records and pixels equal the device-pointer entry points, ragged tail included."""
+    import ctypes as C
+
+    import lrf_b200
+    from lrf_b200 import _cabi, compression
+
+    H, W = shape
+    lib = _cabi.lib()
+    base = torch.stack([port.s_nat(4000 + i, H, W) for i in range(6)])
+    imgs = base[torch.arange(batch) % 6].contiguous()
+    cfg, lay = compression.resolve_plan(H, W, None, 7, "YCbCr", (0.5, 0.5), (8, 8), (-16, 15), 10)
+    want, _, _ = lrf_b200.qmf_encode_batch(imgs, return_records=True, **README_KW)
+    want = want.cpu()
+    ctx = C.c_void_p()
+    _cabi.check(lib.lrfb_ctx_create(0, C.byref(ctx)), "lrfb_ctx_create")
+    try:
+        _cabi.check(lib.lrfb_ctx_set_chunk_bytes(ctx, chunk_images * 3 * H * W), "chunk")
+        h_in = imgs.pin_memory()
+        h_out = torch.empty((batch, lay.record_bytes), dtype=torch.int8).pin_memory()
+        for _ in range(2):  # second call reuses the context's buffers
+            h_out.zero_()
+            _cabi.check(lib.lrfb_qmf_encode_host(ctx, C.byref(cfg), batch, C.c_void_p(h_in.data_ptr()),
+                                                 C.c_void_p(h_out.data_ptr())), "lrfb_qmf_encode_host")
+            assert torch.equal(h_out, want)
+        h_img = torch.empty((batch, 3, H, W), dtype=torch.uint8).pin_memory()
+        _cabi.check(lib.lrfb_qmf_decode_host(ctx, C.byref(cfg), batch, C.c_void_p(h_out.data_ptr()),
+                                             C.c_void_p(h_img.data_ptr())), "lrfb_qmf_decode_host")
+        assert torch.equal(h_img, compression.decode_records(want.cuda(), cfg).cpu())
+    finally:
+        lib.lrfb_ctx_destroy(ctx)
+
+
+@pytest.mark.parametrize("shape", [(128, 192), (512, 768)])
+def test_num_iters_50_matches_live_oracle(gpu, shape):
+    """Ablation end point (experiments/ablation_*/eval.py sweep num_iters up to 50): 50 sweeps, product path vs the
+    oracle port run here."""
+    kw = dict(README_KW, num_iters=50)
+    img = port.s_nat(31, *shape)
+    blob, ref, meta = port.qmf_encode(img, return_factors=True, **kw)
+    cfg = config_for(img, kw, meta["rank"])
+    fac, _, L = gpu.encode(img.numpy()[None], cfg)
+    got = split_record(fac[0], L)
+    diffs = [int((g != r.numpy()).sum()) for g, r in zip(got, ref)]
+    dec = gpu.decode(fac, cfg)[0]
+    assert abs(port.psnr(img, torch.from_numpy(dec)) - port.psnr(img, port.qmf_decode(blob))) <= 0.01, diffs
+    if sum(diffs):  # only a near-tie may separate the trajectories
+        from backends import reference_planes
+
+        near = 0
+        for i, x in enumerate(reference_planes(img, kw)):
+            u0, v0 = port.svd_init(x.unsqueeze(0), meta["rank"][i])
+            near += exact.bcd(x.numpy(), u0.squeeze(0).numpy(), v0.squeeze(0).numpy(), kw["bounds"], 50)[2].near_ties
+        assert near > 0, diffs
+
+
+@pytest.mark.parametrize("kind,shape", [("flat", (64, 96)), ("black", (64, 96)), ("half_flat", (64, 96)),
+                                        ("flat", (512, 768)), ("black", (512, 768)), ("half_flat", (512, 768))])
+def test_degenerate_images_match_oracle(gpu, kind, shape):
+    """Rank-one and all-zero planes (s = 0 in U = XV/s; rank-deficient Gram): factors identical to the
+    oracle's, on the generic kernels (64x96) and on the tensor-core sweeps kernel (512x768)."""
+    pc.check_degenerate_image(gpu, kind, *shape)
+
+
+@pytest.mark.parametrize("shape", [(64, 96), (512, 768)])
+def test_dark_image_below_half_luma(gpu, shape):
+    """Luma entries below 0.5 (the Q8.24 planes of the tensor-core path truncate below 2^-24 there): decoded pixels
+    within 1 LSB or PSNR within 0.01 dB of the oracle."""
+    pc.check_degenerate_image(gpu, "dark", *shape, exact_factors=False)

@@ -35,6 +35,24 @@ def test_repack_golden_factors_is_byte_identical(manifest, name):
     new_meta = compression._metadata(torch.uint8, kw["color_space"], True, kw["bounds"], kw["patch_size"], lay)
     assert json.dumps(new_meta) == json.dumps(meta)
     assert packing.pack_qmf_record(rec, lay, new_meta) == blob
+    # the native thread-pool packer of liblrfb.so (lrfb_qmf_pack_host) writes the same bytes
+    assert compression.pack_records(rec[None], cfg, lay, new_meta) == [blob]
+
+
+def test_native_packer_matches_python_packer_on_random_records():
+    """lrfb_qmf_pack_host (C++ zlib pool) == packing.pack_qmf_record for a ragged batch of random records, any thread
+    count; pure host code, so it runs without a GPU."""
+    build()
+    cfg, lay = compression.resolve_plan(96, 160, None, 7, "YCbCr", (0.5, 0.5), (8, 8), (-16, 15), 10)
+    meta = compression._metadata(torch.uint8, "YCbCr", True, (-16, 15), (8, 8), lay)
+    rng = np.random.default_rng(3)
+    recs = rng.integers(-16, 16, size=(37, lay.record_bytes)).astype(np.int8)
+    recs[5] = 0          # highly compressible
+    recs[6, ::2] = 15
+    want = [packing.pack_qmf_record(recs[i], lay, meta) for i in range(len(recs))]
+    for threads in (0, 1, 3):
+        assert compression.pack_records(recs, cfg, lay, meta, threads) == want
+    assert port.qmf_decode(want[0]).shape == (3, 96, 160)
 
 
 def test_framing_errors_match_reference_behaviour():

@@ -41,6 +41,19 @@ def test_own_svd_init_sign_aligned(sim, manifest, name):
     pc.check_free_running_sign_aligned(sim, manifest, name)
 
 
+def test_product_path_reproduces_lapack_signs_and_reference_factors(sim, manifest):
+    """No hook: the eigen-solver's closed-form sign rule gives LAPACK's signs, so the free-running encode equals the
+    reference's factors (128x192: luma M = 384, chroma M = 96 >= 1.5 N)."""
+    pc.check_product_signs(sim, manifest, "snat9_128x192_q7")
+    pc.check_product_path_identical(sim, manifest, "snat9_128x192_q7")
+
+
+@pytest.mark.parametrize("kind", ["flat", "black", "half_flat"])
+def test_degenerate_images_match_oracle(sim, kind):
+    """Rank-one / all-zero planes (s = 0 in U = XV/s, rank-deficient Gram): identical factors."""
+    pc.check_degenerate_image(sim, kind)
+
+
 @pytest.mark.parametrize("name", ["snat7_45x70_q7", "snat8_101x131_q7", "snat1000_256x384_p4",
                                   "snat1000_128x192_rgb"])
 def test_decode_and_sse_exact(sim, manifest, name):
