@@ -545,7 +545,11 @@ eig_topr_kernel(const double* __restrict__ Gin, int Nrt, int R, double* __restri
     if (r == 0 && M_rows < N) sg = -sg;
     if (have_flips) sg = flips[r];
     if (sign_flip) sg *= (double)sign_flip[(size_t)mat * R + r];
-    const double sig = sqrt(fmax(lam[r], 0.0));
+    // Rank-deficient planes (flat chroma of a grey image: the exact Gram has exact zero eigenvalues): f32 gesdd never
+    // returns an exact zero there but rounding noise of the order eps_f32 * sigma_0 with some orthonormal vector, and the
+    // sweeps then settle on (u_r, v_r) = (0, 1) instead of the (1, hi) that an exactly zero initialisation leads to
+    // (SURVEY H10).  Same order of magnitude here: sigma_r >= 1e-7 sigma_0.
+    const double sig = sqrt(fmax(fmax(lam[r], 0.0), r > 0 ? 1e-14 * fmax(lam[0], 0.0) : 0.0));
     // SVDInit (lrf/factorization/qmf.py:45-52): keep min(R, M, N) triplets, v0 = V_R * sqrt(s) in f32
     const bool kept = r < min(M_rows, N) && sig > 0.0;
     const float s32 = kept ? (float)sig : 0.0f;
@@ -570,6 +574,7 @@ eig_topr_kernel(const double* __restrict__ Gin, int Nrt, int R, double* __restri
 // N = 64 specialisations used by eig64_topr_kernel: same arithmetic as sturm_count / tridiag_inverse_iteration, but
 // fully unrolled so that the loads of d, e^2 and the LU factors run ahead of the recurrences (the generic versions
 // pay a shared-memory round trip per dependent step), and the iterate z lives in registers.
+template <int L>
 __device__ __forceinline__ int sturm_count64(const double* __restrict__ d, const double* __restrict__ e2, double x,
                                              double pivmin) {
   // Scaled minors as in sturm_count, but the scale factor of step i is chosen from the magnitude seen at step i-1
@@ -581,7 +586,7 @@ __device__ __forceinline__ int sturm_count64(const double* __restrict__ d, const
   int cnt = p < 0.0;
   double sc = 1.0;
 #pragma unroll 8
-  for (int i = 1; i < 64; ++i) {
+  for (int i = 1; i < L; ++i) {
     const double ps = p * sc, pms = pm * sc;  // rescaled pair (p_{i-1}, p_{i-2})
     double pn = fma(d[i] - x, ps, -e2[i - 1] * pms);
     pn = fabs(pn) < pivmin * fabs(ps) ? -pivmin * ps : pn;
@@ -593,15 +598,19 @@ __device__ __forceinline__ int sturm_count64(const double* __restrict__ d, const
   return cnt;
 }
 
+// L: size of the (leading) tridiagonal block; zout[L..64) is zero-filled
+template <int L>
 __device__ __forceinline__ void tridiag_inverse_iteration64(const double* __restrict__ d, const double* __restrict__ e,
                                                             double lam, double tnorm, double* __restrict__ zout,
                                                             double* __restrict__ lu, int seed) {
-  constexpr int N = 64;
+  constexpr int N = L;
+#pragma unroll 8
+  for (int i = L; i < 64; ++i) zout[i] = 0.0;
   double* dl = lu;
-  double* dd = lu + N;
-  double* du = lu + 2 * N;
-  double* du2 = lu + 3 * N;
-  double* piv = lu + 4 * N;
+  double* dd = lu + 64;
+  double* du = lu + 2 * 64;
+  double* du2 = lu + 3 * 64;
+  double* piv = lu + 4 * 64;
   const double tol = fmax(tnorm, 1e-300) * 2.3e-16;
   // pivoted LU (dgttrf): the running diagonal / super-diagonal entries are carried in registers
   double ddi = d[0] - lam, dui = e[0];
@@ -694,6 +703,13 @@ struct Eig64Smem {
   double flips[8];
 };
 
+#ifdef LRFB_EIG_TRACE
+__device__ long long g_eig_trace[8];  // probe build only (tools/probes/eig_trace.cu)
+#define EIG_TRACE(pt) if (blockIdx.x == 0 && threadIdx.x == 0) g_eig_trace[pt] = clock64();
+#else
+#define EIG_TRACE(pt)
+#endif
+
 // one-barrier variant: the caller alternates `slot` (0/1) between consecutive uses, so a slow reader of one use never
 // meets the writes of the next
 __device__ __forceinline__ double block64_sum_alt(double v, double* red, int tid, int slot) {
@@ -712,12 +728,59 @@ __device__ __forceinline__ double block64_sum(double v, double* red, int tid) { 
   return s;
 }
 
-#ifdef LRFB_EIG_TRACE
-__device__ long long g_eig_trace[8];  // probe build only (tools/probes/eig_trace.cu)
-#define EIG_TRACE(pt) if (blockIdx.x == 0 && threadIdx.x == 0) g_eig_trace[pt] = clock64();
-#else
-#define EIG_TRACE(pt)
-#endif
+
+// Phases 2-3 of eig64_topr_kernel on the leading L x L block of the tridiagonal in sm.d / sm.e / sm.e2: the R largest
+// eigenvalues (each warp multisects its share) into sm.lam, their eigenvectors (inverse iteration, one thread each)
+// into sm.z (zero beyond L).  Ends with a barrier.
+template <int L>
+__device__ __forceinline__ void eig64_solve(Eig64Smem& sm, int R, int tid, int lane, int warp) {
+  const double* d = sm.d;
+  const double* e = sm.e;
+  double glo = d[0], ghi = d[0], maxe2 = 0.0;
+#pragma unroll 1
+  for (int i = 0; i < L; ++i) {
+    double r = (i > 0 ? fabs(e[i - 1]) : 0.0) + (i < L - 1 ? fabs(e[i]) : 0.0);
+    glo = fmin(glo, d[i] - r);
+    ghi = fmax(ghi, d[i] + r);
+    if (i < L - 1) maxe2 = fmax(maxe2, e[i] * e[i]);
+  }
+  const double tnorm = fmax(fabs(glo), fabs(ghi));
+  const double pivmin = 1e-290 * fmax(1.0, maxe2);
+  glo -= 2.3e-16 * tnorm * L + pivmin;
+  ghi += 2.3e-16 * tnorm * L + pivmin;
+  {
+    const int per_warp = (R + 1) / 2;  // eigenvalues handled by each warp
+    int ppe = 32;
+    while (ppe > 1 && 32 / ppe < per_warp) ppe >>= 1;
+    int rounds = 1;
+    {
+      double shrink = 1.0;
+      while (shrink < 7.0e13) shrink *= (double)(ppe + 1), ++rounds;
+    }
+    const int grp = lane / ppe, pr = lane % ppe;
+    const int r = warp * per_warp + grp;
+    const bool active = grp < per_warp && r < R;
+    const int idx = L - 1 - r;
+    double lo = glo, hi = ghi;
+#pragma unroll 1
+    for (int round = 0; round < rounds; ++round) {
+      const double step = (hi - lo) / (double)(ppe + 1);
+      const double x = lo + step * (double)(pr + 1);
+      const int cnt = active ? sturm_count64<L>(d, sm.e2, x, pivmin) : 0;
+      const unsigned ballot = __ballot_sync(0xffffffffu, active && cnt > idx);
+      const unsigned bits = (ppe == 32) ? ballot : ((ballot >> (grp * ppe)) & ((1u << ppe) - 1u));
+      const int f = bits ? (__ffs((int)bits) - 1) : ppe;
+      const double nlo = (f == 0) ? lo : lo + step * (double)f;
+      const double nhi = (f == ppe) ? hi : lo + step * (double)(f + 1);
+      lo = nlo, hi = nhi;
+    }
+    if (active && pr == 0) sm.lam[r] = 0.5 * (lo + hi);
+  }
+  __syncthreads();
+  EIG_TRACE(2)
+  if (tid < R) tridiag_inverse_iteration64<L>(d, e, sm.lam[tid], tnorm, sm.z + tid * 64, sm.lu + tid * 5 * 64, tid);
+  __syncthreads();
+}
 
 __global__ void __launch_bounds__(64, 6)
 eig64_topr_kernel(double* __restrict__ G, int R, double* __restrict__ evec_out, double* __restrict__ sigma_out,
@@ -735,9 +798,16 @@ eig64_topr_kernel(double* __restrict__ G, int R, double* __restrict__ evec_out, 
   for (int i = 0; i < 4; ++i) sm.g4[i * N + tid] = a[i];  // G[i][tid] = G[tid][i]
 
   EIG_TRACE(0)
-  // ---- 1. tridiagonalisation ----
+  // ---- 1. tridiagonalisation, in two stages ----
+  // The Householder reduction that keeps e_0 fixed IS the Lanczos process started from e_0, and for the patch spectra of
+  // natural images its top Ritz pairs converge within ~20 steps (kodim01 luma: residual 2e-19 lambda_0 at step 20).  So
+  // after kFastSteps steps the top-R pairs of the leading block are tested against the exact residual bound
+  // |z_r[last]| * ||coupling row||; only matrices that fail it (noise images: near-degenerate bulk spectrum) pay for the
+  // remaining steps.  Reflectors that were never formed are identities, the result is the same to ~1e-15 lambda_0.
+  constexpr int kFastSteps = 23, kFastBlock = kFastSteps + 1;
+  auto reduce = [&](int k_begin, int k_end) {
 #pragma unroll 1
-  for (int k = 0; k < N - 2; ++k) {
+  for (int k = k_begin; k < k_end; ++k) {
     if (warp == (k >> 5)) {
       if (tid == k) {
         // column k = row k (symmetric): x and the diagonal; its owner also forms |x_{k+2..}|^2 (no block reduction)
@@ -793,63 +863,41 @@ eig64_topr_kernel(double* __restrict__ G, int R, double* __restrict__ evec_out, 
     }
     // no barrier here: the next step's first writes (xs, red[4]) were last read before this step's second barrier
   }
+  };
+  reduce(0, kFastSteps);
   __syncthreads();
-  if (tid == N - 2) sm.d[N - 2] = a[N - 2], sm.e[N - 2] = a[N - 1], sm.tau[N - 2] = 0.0;
-  if (tid == N - 1) sm.d[N - 1] = a[N - 1], sm.e[N - 1] = 0.0, sm.tau[N - 1] = 0.0;
+  // leading block: d[0..kFastSteps], e[0..kFastSteps); thread kFastSteps holds the next diagonal entry and the coupling row
+  if (tid == kFastSteps) {
+    double q = 0.0;
+#pragma unroll
+    for (int j = 0; j < N; ++j) q = fma(j > kFastSteps ? a[j] : 0.0, a[j], q);
+    sm.d[kFastSteps] = a[kFastSteps], sm.e[kFastSteps] = 0.0, sm.red[5] = sqrt(q);
+  }
   __syncthreads();
   sm.e2[tid] = sm.e[tid] * sm.e[tid];
   __syncthreads();
-
   EIG_TRACE(1)
-  // ---- 2. R largest eigenvalues: each warp multisects its share of the eigenvalues ----
-  const double* d = sm.d;
-  const double* e = sm.e;
-  double glo = d[0], ghi = d[0], maxe2 = 0.0;
-#pragma unroll 1
-  for (int i = 0; i < N; ++i) {
-    double r = (i > 0 ? fabs(e[i - 1]) : 0.0) + (i < N - 1 ? fabs(e[i]) : 0.0);
-    glo = fmin(glo, d[i] - r);
-    ghi = fmax(ghi, d[i] + r);
-    maxe2 = fmax(maxe2, e[i] * e[i]);
-  }
-  const double tnorm = fmax(fabs(glo), fabs(ghi));
-  const double pivmin = 1e-290 * fmax(1.0, maxe2);
-  glo -= 2.3e-16 * tnorm * N + pivmin;
-  ghi += 2.3e-16 * tnorm * N + pivmin;
+  eig64_solve<kFastBlock>(sm, R, tid, lane, warp);
+  int n_refl = kFastSteps;  // reflectors to undo in the back-transformation
   {
-    const int per_warp = (R + 1) / 2;  // eigenvalues handled by each warp
-    int ppe = 32;
-    while (ppe > 1 && 32 / ppe < per_warp) ppe >>= 1;
-    int rounds = 1;
-    {
-      double shrink = 1.0;
-      while (shrink < 7.0e13) shrink *= (double)(ppe + 1), ++rounds;
+    bool converged = true;
+    const double lam0 = fmax(sm.lam[0], 0.0);
+    for (int r = 0; r < R; ++r)
+      if (sm.lam[r] > 1e-14 * lam0)  // components inside the noise floor of a rank-deficient plane are arbitrary anyway
+        converged = converged && sm.red[5] * fabs(sm.z[r * N + kFastSteps]) <= 1e-15 * lam0;
+    if (!converged) {  // uniform: every thread read the same shared values
+      __syncthreads();
+      reduce(kFastSteps, N - 2);
+      __syncthreads();
+      if (tid == N - 2) sm.d[N - 2] = a[N - 2], sm.e[N - 2] = a[N - 1], sm.tau[N - 2] = 0.0;
+      if (tid == N - 1) sm.d[N - 1] = a[N - 1], sm.e[N - 1] = 0.0, sm.tau[N - 1] = 0.0;
+      __syncthreads();
+      sm.e2[tid] = sm.e[tid] * sm.e[tid];
+      __syncthreads();
+      eig64_solve<N>(sm, R, tid, lane, warp);
+      n_refl = N - 2;
     }
-    const int grp = lane / ppe, pr = lane % ppe;
-    const int r = warp * per_warp + grp;
-    const bool active = grp < per_warp && r < R;
-    const int idx = N - 1 - r;
-    double lo = glo, hi = ghi;
-#pragma unroll 1
-    for (int round = 0; round < rounds; ++round) {
-      const double step = (hi - lo) / (double)(ppe + 1);
-      const double x = lo + step * (double)(pr + 1);
-      const int cnt = active ? sturm_count64(d, sm.e2, x, pivmin) : 0;
-      const unsigned ballot = __ballot_sync(0xffffffffu, active && cnt > idx);
-      const unsigned bits = (ppe == 32) ? ballot : ((ballot >> (grp * ppe)) & ((1u << ppe) - 1u));
-      const int f = bits ? (__ffs((int)bits) - 1) : ppe;
-      const double nlo = (f == 0) ? lo : lo + step * (double)f;
-      const double nhi = (f == ppe) ? hi : lo + step * (double)(f + 1);
-      lo = nlo, hi = nhi;
-    }
-    if (active && pr == 0) sm.lam[r] = 0.5 * (lo + hi);
   }
-  __syncthreads();
-
-  EIG_TRACE(2)
-  // ---- 3. eigenvectors of the tridiagonal (one thread each, iterate in registers); cooperative MGS ----
-  if (tid < R) tridiag_inverse_iteration64(d, e, sm.lam[tid], tnorm, sm.z + tid * N, sm.lu + tid * 5 * N, tid);
-  __syncthreads();
   EIG_TRACE(3)
   double zc[4];  // thread c holds element c of each vector
 #pragma unroll
@@ -883,9 +931,10 @@ eig64_topr_kernel(double* __restrict__ G, int R, double* __restrict__ evec_out, 
   EIG_TRACE(4)
   // ---- 4. back-transform: thread c holds element c of each vector and column c of the reflectors ----
 #pragma unroll
-  for (int k = 0; k < N - 2; ++k) a[k] = g[k * N + tid];  // reflector k, element `tid` (written by this thread)
+  for (int k = 0; k < N - 2; ++k) a[k] = k < n_refl ? g[k * N + tid] : 0.0;  // reflector k, element `tid` (written by this thread)
 #pragma unroll
   for (int k = N - 3; k >= 0; --k) {
+    if (k >= n_refl) continue;  // uniform
     const double tk = sm.tau[k];
     const double h = tid > k ? a[k] : 0.0;
     double dot[4];
@@ -970,7 +1019,8 @@ eig64_topr_kernel(double* __restrict__ G, int R, double* __restrict__ evec_out, 
     if (r == 0 && M_rows < N) sg = -sg;
     if (have_flips) sg = sm.flips[r];
     if (sign_flip) sg *= (double)sign_flip[(size_t)mat * R + r];
-    const double sig = sqrt(fmax(sm.lam[r], 0.0));
+    // noise floor of a rank-deficient plane as in eig_topr_kernel: sigma_r >= 1e-7 sigma_0
+    const double sig = sqrt(fmax(fmax(sm.lam[r], 0.0), r > 0 ? 1e-14 * fmax(sm.lam[0], 0.0) : 0.0));
     const bool kept = r < min(M_rows, N) && sig > 0.0;
     const float s32 = kept ? (float)sig : 0.0f;
     const float rs = __fsqrt_rn(s32);

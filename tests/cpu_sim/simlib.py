@@ -26,7 +26,7 @@ def build() -> str:
         return _SO
     os.makedirs(os.path.dirname(_SO), exist_ok=True)
     subprocess.check_call([
-        "g++", "-std=c++20", "-O2", "-pthread", "-DLRFB_SIM", "-ffp-contract=off", "-fvisibility=hidden",
+        "g++", "-std=c++20", "-O2", "-pthread", "-DLRFB_SIM", "-DLRFB_DEV", "-ffp-contract=off", "-fvisibility=hidden",
         "-fPIC", "-shared", "-I", _HERE, "-I", _CSRC, "-x", "c++", os.path.join(_CSRC, "lrfb_api.cu"),
         "-o", _SO, "-lz",
     ])
