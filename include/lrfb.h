@@ -123,7 +123,7 @@ int32_t lrfb_factorize(const float* d_x, int32_t n_mat, int32_t M, int32_t N, in
  * the initialisation v0; d_u holds u0 when d_s0 is NULL, otherwise d_u is output only and the first half-sweep
  * derives u0 = (X v0) / s from d_s0 [n_mat][R] (f32 singular values) exactly as lrfb_qmf_encode does.
  * flags bit 0 (LRFB_X_IN_U8_RANGE): every entry of d_x lies in [0, 256) — true for the planes of the uint8 front
- * end; allows the exact fixed-point tensor-core path for the X^T U half-sweep.  Workspace: at least 32768*R*R bytes. */
+ * end; allows the exact fixed-point tensor-core path for the X^T U half-sweep.  Workspace: at least 592*(2*R*R + N*R)*4 bytes. */
 #define LRFB_X_IN_U8_RANGE 1u
 int32_t lrfb_bcd(const float* d_x, int32_t n_mat, int32_t M, int32_t N, int32_t R, float bound_lo,
                  float bound_hi, int32_t num_iters, float* d_u, float* d_v, const float* d_s0, uint32_t flags,

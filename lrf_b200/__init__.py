@@ -8,12 +8,13 @@ from .compression import (  # noqa: F401
     qmf_encode, qmf_decode, qmf_encode_batch, qmf_decode_batch, qmf_rank, resolve_plan, EncodePlan,
     decode_records, sse_u8, psnr_batch, svd_encode, svd_decode, svd_encode_batch,
 )
-from .evaluation import eval_compression, eval_qmf_batch  # noqa: F401
+from .evaluation import eval_compression, eval_qmf_batch, eval_dataset, read_image  # noqa: F401
 from .factorization import QMF  # noqa: F401
 from .metrics import psnr, mse, bits_per_pixel, compression_ratio, get_memory_usage  # noqa: F401
 from .packing import combine_bytes, separate_bytes, dict_to_bytes, bytes_to_dict  # noqa: F401
 
 __all__ = [
     "qmf_encode", "qmf_decode", "svd_encode", "svd_decode", "qmf_encode_batch", "qmf_decode_batch", "qmf_rank", "QMF", "psnr", "mse",
-    "bits_per_pixel", "compression_ratio", "combine_bytes", "separate_bytes",
+    "bits_per_pixel", "compression_ratio", "combine_bytes", "separate_bytes", "eval_compression", "eval_dataset",
+    "read_image",
 ]

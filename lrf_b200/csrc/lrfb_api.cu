@@ -183,7 +183,7 @@ struct FactorWs {  // scratch beyond x/u/v/gram/evec/sigma
     int64_t b = 0;
     if (split > 1) b += align_up((int64_t)n_mat * split * N * N * 8, 256);
     b += align_up((int64_t)n_mat * (int64_t)EigScratch::doubles(N, R) * 8, 256);
-    b += align_up((int64_t)4096 * 2 * R * R * 4, 256);  // bcd_generic bwork
+    b += align_up((int64_t)kGenGrid * gen_scratch_floats(N, R) * 4, 256);  // bcd_generic scratch
     return b;
   }
 };
@@ -441,7 +441,7 @@ int run_bcd(const BcdBatch& b0, int N, int R, float* bwork, cudaStream_t st, int
       default: return launch_bcd_fast<4>(b, st);
     }
   }
-  int grid = std::min(b.n_mat, 4096);
+  int grid = std::min(b.n_mat, kGenGrid);
   LRFB_LAUNCH(bcd_generic_kernel, dim3(grid), dim3(256), 0, st, b, N, R, bwork);
   return check_launch("bcd_generic_kernel");
 }
@@ -860,7 +860,7 @@ LRFB_EXPORT int32_t lrfb_bcd(const float* d_x, int32_t n_mat, int32_t M, int32_t
   if (R > kGenMaxR || N > 1024) return fail(LRFB_E_UNSUPPORTED, "N=%d R=%d not implemented", N, R);
   int rc = check_bounds(bound_lo, bound_hi);
   if (rc) return rc;
-  if (workspace_bytes < (int64_t)4096 * 2 * R * R * 4 || !d_workspace)
+  if (workspace_bytes < (int64_t)kGenGrid * gen_scratch_floats(N, R) * 4 || !d_workspace)
     return fail(LRFB_E_WORKSPACE, "workspace too small");
   BcdBatch b;
   b.X = d_x, b.x_stride = (long long)M * N, b.U = d_u, b.V = d_v, b.Uq = nullptr, b.Vq = nullptr;
