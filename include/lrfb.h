@@ -35,7 +35,7 @@ extern "C" {
 #define LRFB_F32 1
 
 /* Parameters of lrf.qmf_encode (lrf/compression/qmf.py:116-127) after the host resolved the
- * rank rule (:215-225, :244-250).  patch=True branches only. */
+ * rank rule (:215-225, :244-250).  patch=True branches (patch=False: lrfb_qmf_frontend with 1x1 patches + lrfb_factorize). */
 typedef struct lrfb_qmf_config {
   int32_t height, width;    /* image (3, H, W) */
   int32_t patch_h, patch_w; /* patch_size */
@@ -102,6 +102,16 @@ int32_t lrfb_qmf_encode(const lrfb_qmf_config* cfg, int32_t batch, const void* d
  * d_images: [batch][3][H][W] uint8. */
 int32_t lrfb_qmf_decode(const lrfb_qmf_config* cfg, int32_t batch, const int8_t* d_factors, uint8_t* d_images,
                         void* stream);
+
+/* Replaces lrf.qmf_decode for patch=False streams after the byte un-packing (lrf/compression/qmf.py:303-311 RGB,
+ * :339-351 YCbCr): QMF.reconstruct of whole-channel factors, chroma_upsampling(nearest), ycbcr_to_rgb, to_dtype(uint8).
+ * Factors are row-major with their batch dimension, as the reference stores them: YCbCr: d_u[pl] [batch][h_pl][R_pl],
+ * d_v[pl] [batch][w_pl][R_pl] for pl = Y, Cb, Cr (chroma planes chroma_h x chroma_w); RGB: d_u[0] [batch][3][H][R],
+ * d_v[0] [batch][3][W][R].  The encode side of these branches is lrfb_qmf_frontend (1x1 "patches" give the planes)
+ * followed by lrfb_factorize per plane. */
+int32_t lrfb_qmf_decode_planes(int32_t color_space, int32_t height, int32_t width, int32_t chroma_h, int32_t chroma_w,
+                               const int32_t* rank, int32_t batch, const int8_t* const* d_u, const int8_t* const* d_v,
+                               uint8_t* d_images, void* stream);
 
 /* Stage-level: only the front end (compression/utils.py:24-47, :76-95, :108-132, compression/qmf.py:43-56).
  * d_x: f32, plane-major [plane][batch][rows][cols] packed (offsets = workspace map x[] minus x[0]). */

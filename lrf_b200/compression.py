@@ -164,8 +164,6 @@ class EncodePlan:
 def _check_encode_args(rank, quality, color_space, patch, dtype, kwargs, bounds=None):
     assert (rank, quality) != (None, None), "Either 'rank' or 'quality' must be specified."
     assert color_space in ("RGB", "YCbCr"), "`color_space` must be one of 'RGB' or 'YCbCr'."
-    if not patch:
-        raise NotImplementedError("lrf_b200: patch=False is not on the accelerated path (SURVEY §8f.3)")
     if dtype != torch.int8:
         raise NotImplementedError("lrf_b200: only dtype=torch.int8 factors are implemented")
     if bounds is not None and (math.ceil(bounds[0]) < -128 or math.floor(bounds[1]) > 127):
@@ -191,6 +189,9 @@ def qmf_encode_batch(images: torch.Tensor, rank=None, quality=None, color_space:
     _check_encode_args(rank, quality, color_space, patch, dtype, kwargs, bounds)
     _require_cuda()
     assert images.ndim == 4 and images.shape[1] == 3, "images must be (B, 3, H, W)"
+    if not patch:
+        assert not return_records, "patch=False factors are not stored as patch records"
+        return _qmf_encode_nopatch(images, rank, quality, color_space, scale_factor, bounds, kwargs.get("num_iters", 10))
     device = images.device if images.is_cuda else torch.device("cuda", torch.cuda.current_device())
     dev_images, in_dtype = _to_device_images(images, device)
     B, _, H, W = images.shape
@@ -213,6 +214,88 @@ def qmf_encode(image: torch.Tensor, rank=None, quality=None, color_space: str = 
     _check_encode_args(rank, quality, color_space, patch, dtype, kwargs)
     return qmf_encode_batch(image.unsqueeze(0), rank, quality, color_space, scale_factor, patch, patch_size,
                             bounds, dtype, **kwargs)[0]
+
+
+def _rank_rule(rows: int, cols: int, quality) -> int:
+    assert quality >= 0 and quality <= 100, "'quality' must be between 0 and 100."
+    return max(round(min(rows, cols) * quality / 100), 1)
+
+
+def _qmf_encode_nopatch(images, rank, quality, color_space, scale_factor, bounds, num_iters) -> list[bytes]:
+    """The patch=False branches of ``qmf_encode`` (lrf/compression/qmf.py:195-212 RGB, :264-286 YCbCr): every channel
+    is factorised as one H x W matrix.  Planes come from the front-end kernels (1 x 1 "patches" are the planes
+    themselves), the factorisation from lrfb_factorize (generic kernels: N up to 1024, R up to 64); the 3-D factors
+    keep their batch dimension and go through the N-D branch of encode_tensor, as in the reference."""
+    from .factorization import QMF
+
+    device = images.device if images.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    dev_images, in_dtype = _to_device_images(images, device)
+    B, _, H, W = images.shape
+    meta = {"dtype": str(images.dtype).split(".")[-1], "color space": color_space, "patch": False, "bounds": bounds}
+    with torch.cuda.device(device):
+        if color_space == "RGB":
+            R = _rank_rule(H, W, quality) if rank is None else rank
+            meta["rank"] = R
+            u, v, _ = QMF(rank=R, num_iters=num_iters, bounds=bounds).decompose(dev_images.float())
+            fac = [(u.to(torch.int8).cpu().numpy(), v.to(torch.int8).cpu().numpy())]  # (B,3,H,R), (B,3,W,R)
+        else:
+            cfg = _cabi.make_config(H, W, (1, 1), "YCbCr", in_dtype, scale_factor, (1, 1, 1), bounds, 1)
+            lay, m = _cabi.QmfLayout(), _cabi.QmfWorkspaceMap()
+            _cabi.check(_cabi.lib().lrfb_qmf_layout_query(C.byref(cfg), C.byref(lay)), "lrfb_qmf_layout_query")
+            _cabi.check(_cabi.lib().lrfb_qmf_workspace_query(C.byref(cfg), B, C.byref(m)), "lrfb_qmf_workspace_query")
+            x = torch.empty(m.u[0] - m.x[0], dtype=torch.uint8, device=device)  # the three planes, plane-major
+            rc = _cabi.lib().lrfb_qmf_frontend(C.byref(cfg), B, C.c_void_p(dev_images.data_ptr()),
+                                               C.c_void_p(x.data_ptr()), _stream_ptr())
+            _cabi.check(rc, "lrfb_qmf_frontend")
+            rk = _triple(rank, lambda r: max(r // 2, 1))
+            ql = _triple(quality, lambda q: q / 2)
+            meta["original size"], meta["rank"], fac = [], [], []
+            for pl in range(3):
+                h, w = lay.orig_h[pl], lay.orig_w[pl]
+                R = _rank_rule(h, w, ql[pl]) if rk[pl] is None else rk[pl]
+                meta["original size"].append([h, w])
+                meta["rank"].append(R)
+                off = m.x[pl] - m.x[0]
+                plane = x[off : off + B * h * w * 4].view(torch.float32).view(B, 1, h, w)
+                u, v, _ = QMF(rank=R, num_iters=num_iters, bounds=bounds).decompose(plane)
+                fac.append((u.to(torch.int8).cpu().numpy(), v.to(torch.int8).cpu().numpy()))  # (B,1,h,R), (B,1,w,R)
+    mj = packing.dict_to_bytes(meta)
+
+    def pack(i):
+        parts = []
+        for u, v in fac:
+            parts += [packing.encode_tensor_nd(u[i]), packing.encode_tensor_nd(v[i])]
+        return packing.combine_bytes([mj, packing.combine_bytes(parts)])
+
+    return list(_pool().map(pack, range(B)))
+
+
+def _qmf_decode_nopatch(metas, bodies, device) -> torch.Tensor:
+    """patch=False streams of one shape → uint8 (B,3,H,W) on the device (lrfb_qmf_decode_planes)."""
+    meta = metas[0]
+    ycbcr = meta["color space"] == "YCbCr"
+    n_pl = 3 if ycbcr else 1
+    parsed = [[packing.decode_tensor(b) for b in packing.separate_bytes(body, 2 * n_pl)] for body in bodies]
+    B = len(parsed)
+    us = [np.stack([p[2 * pl] for p in parsed]) for pl in range(n_pl)]
+    vs = [np.stack([p[2 * pl + 1] for p in parsed]) for pl in range(n_pl)]
+    if ycbcr:
+        (H, W), (ch, cw) = meta["original size"][0], meta["original size"][1]
+        ranks = list(meta["rank"])
+    else:
+        H, W, ch, cw = us[0].shape[-2], vs[0].shape[-2], 0, 0
+        ranks = [meta["rank"]]
+    with torch.cuda.device(device):
+        du = [torch.from_numpy(np.ascontiguousarray(a, np.int8)).to(device) for a in us]
+        dv = [torch.from_numpy(np.ascontiguousarray(a, np.int8)).to(device) for a in vs]
+        out = torch.empty((B, 3, H, W), dtype=torch.uint8, device=device)
+        pu = (C.c_void_p * 3)(*[t.data_ptr() for t in du] + [None] * (3 - n_pl))
+        pv = (C.c_void_p * 3)(*[t.data_ptr() for t in dv] + [None] * (3 - n_pl))
+        rk = (C.c_int32 * 3)(*(ranks + [0] * (3 - n_pl)))
+        rc = _cabi.lib().lrfb_qmf_decode_planes(_cabi.LRFB_YCBCR if ycbcr else _cabi.LRFB_RGB, H, W, ch, cw, rk, B,
+                                                pu, pv, C.c_void_p(out.data_ptr()), _stream_ptr())
+        _cabi.check(rc, "lrfb_qmf_decode_planes")
+        return out
 
 
 def _parse_encoded(encoded: bytes):
@@ -262,6 +345,12 @@ def qmf_decode_batch(encoded: list[bytes], device=None) -> torch.Tensor:
     """Batched ``qmf_decode`` of equally shaped streams → uint8 (B,3,H,W) on the device."""
     _require_cuda()
     device = device or torch.device("cuda", torch.cuda.current_device())
+    heads = [packing.separate_bytes(e, 2) for e in encoded]
+    metas = [packing.bytes_to_dict(h[0]) for h in heads]
+    if not metas[0]["patch"]:
+        if metas[0]["dtype"] != "uint8":
+            raise NotImplementedError("lrf_b200: only uint8 images are decoded on the CUDA path")
+        return _qmf_decode_nopatch(metas, [h[1] for h in heads], device)
     parsed = list(_pool().map(_parse_encoded, encoded))
     cfg, lay = _decode_config(parsed[0][0])
     host = np.empty((len(encoded), lay.record_bytes), np.int8)

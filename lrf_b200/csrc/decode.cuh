@@ -86,6 +86,54 @@ qmf_decode_kernel(const int8_t* __restrict__ factors, unsigned char* __restrict_
 
 
 // ---------------------------------------------------------------------------------------------------
+// patch=False streams (lrf/compression/qmf.py:303-311 RGB, :339-344 YCbCr): every plane is U V^T of whole-channel
+// factors kept row-major with their leading batch dimension, u [n_img][(3)][h][R], v [n_img][(3)][w][R].
+// ---------------------------------------------------------------------------------------------------
+struct PlanesParams {
+  int H, W, ch, cw, ycbcr, n_img;
+  int rank[3];
+  const int8_t* u[3];
+  const int8_t* v[3];
+};
+
+__device__ __forceinline__ float uv_dot(const int8_t* __restrict__ u, const int8_t* __restrict__ v, int R) {
+  float acc = 0.0f;  // small integers: exact in f32 in any order
+  for (int r = 0; r < R; ++r) acc = __fadd_rn(acc, __fmul_rn((float)u[r], (float)v[r]));
+  return acc;
+}
+
+__global__ void __launch_bounds__(256)
+qmf_decode_planes_kernel(unsigned char* __restrict__ out, PlanesParams P) {
+  const float t[3][3] = {{1.0f, 0.0f, 1.40200f}, {1.0f, -0.344136f, -0.714136f}, {1.0f, 1.77200f, 0.0f}};
+  const size_t hw = (size_t)P.H * P.W;
+  for (int im = blockIdx.y; im < P.n_img; im += gridDim.y) {
+    unsigned char* o = out + (size_t)im * 3 * hw;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < hw; e += (size_t)gridDim.x * blockDim.x) {
+      const int y = (int)(e / P.W), x = (int)(e - (size_t)y * P.W);
+      if (!P.ycbcr) {
+        const int R = P.rank[0];
+        for (int c = 0; c < 3; ++c)
+          o[c * hw + e] = to_u8_trunc(uv_dot(P.u[0] + (((size_t)im * 3 + c) * P.H + y) * R,
+                                            P.v[0] + (((size_t)im * 3 + c) * P.W + x) * R, R));
+        continue;
+      }
+      const int sy = nearest_src(y, P.ch, P.H), sx = nearest_src(x, P.cw, P.W);
+      float ycc[3];
+      ycc[0] = __fadd_rn(uv_dot(P.u[0] + ((size_t)im * P.H + y) * P.rank[0], P.v[0] + ((size_t)im * P.W + x) * P.rank[0], P.rank[0]), 0.0f);
+      ycc[1] = __fadd_rn(uv_dot(P.u[1] + ((size_t)im * P.ch + sy) * P.rank[1], P.v[1] + ((size_t)im * P.cw + sx) * P.rank[1], P.rank[1]), -128.0f);
+      ycc[2] = __fadd_rn(uv_dot(P.u[2] + ((size_t)im * P.ch + sy) * P.rank[2], P.v[2] + ((size_t)im * P.cw + sx) * P.rank[2], P.rank[2]), -128.0f);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float acc = __fmul_rn(t[c][0], ycc[0]);
+        acc = __fmaf_rn(t[c][1], ycc[1], acc);
+        acc = __fmaf_rn(t[c][2], ycc[2], acc);
+        o[c * hw + e] = to_u8_trunc(acc);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Fast path: YCbCr, 8x8 patches, W % 16 == 0, chroma width == W/2.  One thread reconstructs 8
 // consecutive pixels of one image row: they lie in one luma patch row and 4 consecutive elements of one
 // chroma patch row, so the factors are read as 8-byte / 4-byte vectors and each colour plane gets one

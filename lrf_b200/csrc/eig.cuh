@@ -16,7 +16,7 @@
 
 namespace lrfb {
 
-constexpr int kEigMaxR = 32;
+constexpr int kEigMaxR = 64;
 
 struct EigScratch {  // per matrix (doubles): d, e, tau, vv, w [5N] | lam [32] | z [R][N] | lu [R][5N] | g4, p4 [8N]
   static __host__ __device__ size_t doubles(int N, int R) {

@@ -192,6 +192,9 @@ template <int BPT>
 void launch_gram(const float* x, long long xs, int M, int N, double* out, int split, int n_mat, int threads,
                  int nblocks, cudaStream_t st) {
   size_t smem = (size_t)kGramTileRows * ((N + 3) & ~3) * 8;
+#ifndef LRFB_SIM
+  if (smem > 48 * 1024) cudaFuncSetAttribute(gram_kernel<BPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#endif
   int gz = (nblocks + threads * BPT - 1) / (threads * BPT);
   LRFB_LAUNCH(gram_kernel<BPT>, dim3(split, n_mat, gz), dim3(threads), smem, st, x, xs, M, N, out, split);
 }
@@ -912,6 +915,28 @@ LRFB_EXPORT int32_t lrfb_qmf_decode(const lrfb_qmf_config* cfg, int32_t batch, c
   }
   LRFB_LAUNCH(qmf_decode_kernel, grid, dim3(256), 0, (cudaStream_t)(uintptr_t)stream, d_factors, d_images, P);
   return check_launch("qmf_decode_kernel");
+}
+
+LRFB_EXPORT int32_t lrfb_qmf_decode_planes(int32_t color_space, int32_t height, int32_t width, int32_t chroma_h,
+                                           int32_t chroma_w, const int32_t* rank, int32_t batch,
+                                           const int8_t* const* d_u, const int8_t* const* d_v, uint8_t* d_images,
+                                           void* stream) {
+  if (!rank || !d_u || !d_v || !d_images || batch <= 0 || height <= 0 || width <= 0)
+    return fail(LRFB_E_ARG, "bad arguments");
+  if (color_space != LRFB_RGB && color_space != LRFB_YCBCR) return fail(LRFB_E_ARG, "bad color_space");
+  PlanesParams P;
+  memset(&P, 0, sizeof(P));
+  P.H = height, P.W = width, P.ch = chroma_h, P.cw = chroma_w, P.ycbcr = color_space == LRFB_YCBCR, P.n_img = batch;
+  const int n_pl = P.ycbcr ? 3 : 1;
+  for (int pl = 0; pl < n_pl; ++pl) {
+    if (!d_u[pl] || !d_v[pl] || rank[pl] <= 0) return fail(LRFB_E_ARG, "plane %d: null factor or bad rank", pl);
+    P.u[pl] = d_u[pl], P.v[pl] = d_v[pl], P.rank[pl] = rank[pl];
+  }
+  if (P.ycbcr && (chroma_h <= 0 || chroma_w <= 0)) return fail(LRFB_E_ARG, "bad chroma size");
+  const long long hw = (long long)height * width;
+  dim3 grid((unsigned)std::min<long long>((hw + 255) / 256, 8192), std::min(batch, 65535));
+  LRFB_LAUNCH(qmf_decode_planes_kernel, grid, dim3(256), 0, (cudaStream_t)(uintptr_t)stream, d_images, P);
+  return check_launch("qmf_decode_planes_kernel");
 }
 
 LRFB_EXPORT int32_t lrfb_svd_encode(const lrfb_qmf_config* cfg, int32_t batch, const void* d_images,

@@ -58,7 +58,7 @@ def eval_qmf_batch(images: torch.Tensor, **kwargs) -> dict:
     ref = images.to(decoded.device)
     hw = images.shape[-2] * images.shape[-1]
     return {
-        "bit rate (bpp)": torch.tensor([len(e) * 8 / hw for e in encoded]),
+        "bit rate (bpp)": torch.tensor([len(e) * 8 / hw for e in encoded], dtype=torch.float64),
         "PSNR (dB)": compression.psnr_batch(decoded, ref).cpu(),
         "encoded": encoded,
     }

@@ -69,6 +69,24 @@ def decode_fibers(blob: bytes) -> np.ndarray:
     return np.stack([np.frombuffer(zlib.decompress(c), dtype=np.dtype(meta["dtype"])) for c in cols], axis=0)
 
 
+def encode_tensor_nd(arr: np.ndarray, level: int = 9) -> bytes:
+    """The N-D branch of encode_tensor (lrf/compression/utils.py:429-455): one zlib stream of the raw buffer behind a
+    {"shape", "dtype"} header — what the patch=False branches of qmf_encode emit for their 3-D factors."""
+    arr = np.ascontiguousarray(arr)
+    meta = {"shape": list(arr.shape), "dtype": str(arr.dtype)}
+    return combine_bytes([dict_to_bytes(meta), zlib.compress(arr.tobytes(), level)])
+
+
+def decode_tensor(blob: bytes) -> np.ndarray:
+    """decode_tensor (lrf/compression/utils.py:458-490): column-wise matrices come back as (rows, R), N-D tensors in
+    their stored shape."""
+    meta_b, body = separate_bytes(blob)
+    meta = bytes_to_dict(meta_b)
+    if "num_fibers" in meta:
+        return np.ascontiguousarray(decode_fibers(blob).T)
+    return np.frombuffer(zlib.decompress(body), dtype=np.dtype(meta["dtype"])).reshape(meta["shape"])
+
+
 def pack_qmf_record(record: np.ndarray, layout, metadata: dict) -> bytes:
     """One image's int8 factor record (lrfb_qmf_layout order) + metadata → encoded bytes."""
     blobs = []

@@ -240,6 +240,25 @@ def decode_matrix(blob: bytes) -> torch.Tensor:
 # --------------------------------------------------------------------------------------
 
 
+def encode_tensor(t: torch.Tensor) -> bytes:
+    """lrf/compression/utils.py:429-455 — 2-D tensors go column-wise through encode_matrix, anything else is one
+    zlib stream of the raw buffer with a {"shape", "dtype"} header (the patch=False branches produce 3-D factors)."""
+    if t.ndim == 2:
+        return encode_matrix(t)
+    meta = {"shape": t.shape, "dtype": str(t.dtype).split(".")[-1]}
+    return combine_bytes([json.dumps(meta).encode("utf-8"), zlib.compress(t.numpy().tobytes(), 9)])
+
+
+def decode_tensor(blob: bytes) -> torch.Tensor:
+    """lrf/compression/utils.py:458-490."""
+    meta_b, body = separate_bytes(blob, 2)
+    meta = json.loads(meta_b.decode("utf-8"))
+    if "num_fibers" in meta:
+        return decode_matrix(blob)
+    arr = np.frombuffer(zlib.decompress(body), dtype=np.dtype(meta["dtype"])).reshape(meta["shape"])
+    return torch.from_numpy(arr)
+
+
 def _triple(v, halve):
     if isinstance(v, Iterable):
         return tuple(v)
@@ -269,16 +288,35 @@ def qmf_encode(
     patch_size=(8, 8), bounds=(-16, 15), dtype=torch.int8, num_iters=10, return_factors=False,
     inits=None, faithful_cost=True,
 ):
-    """lrf/compression/qmf.py:116-292, YCbCr + patch branch and RGB + patch branch."""
+    """lrf/compression/qmf.py:116-292: YCbCr / RGB, patch=True (:164-193, :227-262) and patch=False (:195-212,
+    :264-286: whole channels as matrices, factors keep their leading batch dimension and go through the N-D branch of
+    encode_tensor)."""
     assert (rank, quality) != (None, None), "Either 'rank' or 'quality' must be specified."
     assert color_space in ("RGB", "YCbCr"), "`color_space` must be one of 'RGB' or 'YCbCr'."
-    if not patch:
-        raise NotImplementedError("oracle covers the patch=True branches (SURVEY §8f.3)")
     meta = {
         "dtype": str(image.dtype).split(".")[-1], "color space": color_space,
         "patch": patch, "bounds": bounds,
     }
     factors = []
+    if not patch:
+        if color_space == "RGB":
+            x = image.float()
+            r = rank_rule(*x.shape[-2:], quality) if rank is None else rank
+            meta["rank"] = r
+            u, v = qmf_decompose(x.unsqueeze(0), r, bounds, num_iters, faithful_cost=faithful_cost)
+            factors = [u.squeeze(0).to(dtype), v.squeeze(0).to(dtype)]
+        else:
+            ranks = _triple(rank, lambda r: max(r // 2, 1))
+            quals = _triple(quality, lambda q: q / 2)
+            meta["original size"], meta["rank"] = [], []
+            for i, ch in enumerate(chroma_downsample(rgb_to_ycbcr(image.float()), scale_factor)):
+                r = rank_rule(*ch.shape[-2:], quals[i]) if ranks[i] is None else ranks[i]
+                meta["original size"].append(ch.shape[-2:])
+                meta["rank"].append(r)
+                u, v = qmf_decompose(ch.unsqueeze(0), r, bounds, num_iters, faithful_cost=faithful_cost)
+                factors += [u.squeeze(0).to(dtype), v.squeeze(0).to(dtype)]
+        blob = combine_bytes([json.dumps(meta).encode("utf-8"), combine_bytes([encode_tensor(f) for f in factors])])
+        return (blob, factors, meta) if return_factors else blob
     if color_space == "RGB":
         xp = pad_image(image.float(), patch_size)
         x = patchify(xp, patch_size)
@@ -308,9 +346,18 @@ def qmf_encode(
 
 
 def qmf_decode(blob: bytes) -> torch.Tensor:
-    """lrf/compression/qmf.py:295-353 (patch branches)."""
+    """lrf/compression/qmf.py:295-353."""
     meta_b, body = separate_bytes(blob, 2)
     meta = json.loads(meta_b.decode("utf-8"))
+    if not meta["patch"]:
+        if meta["color space"] == "RGB":
+            u, v = (decode_tensor(b).float() for b in separate_bytes(body, 2))
+            img = u @ v.mT
+        else:
+            fs = [decode_tensor(b).float() for b in separate_bytes(body, 6)]
+            planes = [fs[2 * i] @ fs[2 * i + 1].mT for i in range(3)]
+            img = ycbcr_to_rgb(chroma_upsample(planes, size=meta["original size"][0]))
+        return to_dtype(img, getattr(torch, meta["dtype"]))
     if meta["color space"] == "RGB":
         u, v = (decode_matrix(b).float() for b in separate_bytes(body, 2))
         img = unpad_image(depatchify(u @ v.mT, meta["padded size"], meta["patch size"]),

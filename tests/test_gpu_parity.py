@@ -385,3 +385,24 @@ def test_dark_image_below_half_luma(gpu, shape):
     """Luma entries below 0.5 (the Q8.24 planes of the tensor-core path truncate below 2^-24 there): decoded pixels
     within 1 LSB or PSNR within 0.01 dB of the oracle."""
     pc.check_degenerate_image(gpu, "dark", *shape, exact_factors=False)
+
+
+@pytest.mark.parametrize("name", ["snat1000_128x192_nopatch", "snat1000_96x160_nopatch_rgb"])
+def test_patch_false_branches(manifest, name):
+    """patch=False (lrf/compression/qmf.py:195-212, :264-286, :303-344): whole channels as matrices.  The decoder is
+    bit-exact on the reference's stream; the encoder's stream decodes identically on both decoders and lands within the
+    sign-ambiguity band of the reference (wide matrices, R > 4: LAPACK's signs are not modelled there)."""
+    import lrf_b200
+
+    e = manifest["cases"][name]
+    img = golden_image(e["image"])
+    ref_blob = golden_bytes(name)
+    assert hashlib.sha256(lrf_b200.qmf_decode(ref_blob).numpy().tobytes()).hexdigest() == e["decoded_sha256"]
+    blob = lrf_b200.qmf_encode(img, **golden_kwargs(e))
+    dec = lrf_b200.qmf_decode(blob)
+    assert torch.equal(dec, port.qmf_decode(blob))
+    psnr = port.psnr(img, dec)
+    print(f"\n[patch=False] {name}: bytes {len(blob)} vs {e['bytes']}, psnr {psnr:.4f} vs {e['psnr']:.4f}")
+    assert abs(psnr - e["psnr"]) <= 0.15 and abs(len(blob) - e["bytes"]) <= 0.03 * e["bytes"]
+    meta = lrf_b200.bytes_to_dict(lrf_b200.separate_bytes(blob, 2)[0])
+    assert meta == lrf_b200.bytes_to_dict(lrf_b200.separate_bytes(ref_blob, 2)[0])

@@ -72,4 +72,18 @@ def test_argument_errors_match_reference():
     with pytest.raises(AssertionError):
         compression.qmf_encode(img, quality=7, color_space="HSV")
     with pytest.raises(NotImplementedError):
-        compression.qmf_encode(img, quality=7, patch=False)
+        compression.qmf_encode(img, quality=7, dtype=torch.int16)
+
+
+def test_nd_tensor_framing_matches_reference_layout(manifest):
+    """patch=False streams: the N-D branch of encode_tensor / decode_tensor (lrf/compression/utils.py:429-490)."""
+    blob = golden_bytes("snat1000_128x192_nopatch")
+    meta_b, body = packing.separate_bytes(blob, 2)
+    meta = packing.bytes_to_dict(meta_b)
+    assert meta["patch"] is False and meta["rank"] == [9, 2, 2]
+    parts = packing.separate_bytes(body, 6)
+    facs = [packing.decode_tensor(b) for b in parts]
+    assert facs[0].shape == (1, 128, 9) and facs[1].shape == (1, 192, 9) and facs[2].shape == (1, 64, 2)
+    assert [packing.encode_tensor_nd(f) for f in facs] == list(parts)
+    ref = [f.numpy() for f in (port.decode_tensor(b) for b in parts)]
+    assert all(np.array_equal(a, b) for a, b in zip(facs, ref))

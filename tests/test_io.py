@@ -23,7 +23,7 @@ def test_eval_dataset_and_path_argument(manifest):
     e = manifest["cases"]["kodim01_q7"]
     rows = lrf_b200.eval_dataset(GOLD, qualities=(7,))
     assert len(rows) == 1 and rows[0]["data"] == "kodim01" and rows[0]["method"] == "QMF"
-    assert abs(rows[0]["PSNR (dB)"] - e["psnr"]) <= 0.01 and abs(rows[0]["bit rate (bpp)"] - e["bpp"]) <= 1e-9
+    assert abs(rows[0]["PSNR (dB)"] - e["psnr"]) <= 0.01 and abs(rows[0]["bit rate (bpp)"] - e["bpp"]) <= 1e-7
     out = lrf_b200.eval_compression(os.path.join(GOLD, "kodim01.png"), lrf_b200.qmf_encode, lrf_b200.qmf_decode,
                                     quality=7, num_iters=10)
-    assert abs(out["bit rate (bpp)"] - e["bpp"]) <= 1e-9
+    assert abs(out["bit rate (bpp)"] - e["bpp"]) <= 1e-7

@@ -73,6 +73,10 @@ def main():
     add("snat1000_256x384_rank", base, kw={**{k: v for k, v in README_KW.items() if k != "quality"},
                                           "rank": 6})
     add("snat1000_128x192_rgb", ("s_nat", 1000, 128, 192), kw={**README_KW, "color_space": "RGB", "quality": 3})
+    # patch=False branches (lrf/compression/qmf.py:195-212, :264-286): whole channels as matrices
+    add("snat1000_128x192_nopatch", ("s_nat", 1000, 128, 192), kw={**README_KW, "patch": False})
+    add("snat1000_96x160_nopatch_rgb", ("s_nat", 1000, 96, 160),
+        kw={**README_KW, "patch": False, "color_space": "RGB", "quality": 5})
     add("kodim01_svd_q1", ("png", "kodim01.png"), codec="svd", kw=dict(quality=1.0))
     add("kodim01_svd_q7", ("png", "kodim01.png"), codec="svd", kw=dict(quality=7))
     add("snat1000_512x768_svd_q1", ("s_nat", 1000, 512, 768), codec="svd", kw=dict(quality=1.0))
