@@ -132,7 +132,9 @@ __device__ long long g_tc_trace[16 * 12];  // probe build only (tools/probes/tc_
 #define TC_TRACE_S(pt)
 #endif
 
-template <int R, int ROWS, int NT>
+template <int R, int ROWS, int NT, int MAXC = (ROWS > 384 ? 8 : 16)>
+// MAXC: largest cluster the instantiation is launched with (sizes the unrolled slot loops).  768-row CTAs in clusters
+// of 16 (non-portable size) keep matrices of up to 12 288 rows resident: kodim01's 10 292-row luma plane.
 // 384-row shape: 2 CTAs per SM, so the exchange latency of one overlaps the arithmetic of the other.  Its 6 warps land
 // 2,2,1,1 on the four scheduler partitions, so two CTAs put 4 warps on one partition's 16K registers: <= 128 registers
 // per thread (bound declared as 256 threads x 2 CTAs).
@@ -143,7 +145,7 @@ bcd_tc_kernel(BcdBatch P, int cluster_size, int rows_per_cta, const __grid_const
   constexpr int kTcColsA = ROWS / 4;                        // TMEM columns per A block (4 rows per cell)
   constexpr int kTcD1 = 2 * kTcColsA + 16, kTcD2 = kTcD1 + 16, kTcD3 = kTcD2 + 16;  // accumulator columns
   constexpr int kTmemCols = ROWS > 384 ? 512 : 256;
-  constexpr int kMaxC = ROWS > 384 ? 8 : 16;  // largest cluster this shape is launched with
+  constexpr int kMaxC = MAXC;  // largest cluster this instantiation is launched with
   static_assert(ROWS % NT == 0 && ROWS % 64 == 0 && NW >= 4 && kTcD3 + 8 <= kTmemCols, "shape");
   using S = TcSmem<R, ROWS, NT>;
   LRFB_DYN_SMEM(smem_raw);

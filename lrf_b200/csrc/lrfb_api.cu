@@ -302,13 +302,14 @@ bool make_x_tensor_map(const BcdBatch& b, CUtensorMap* out) {
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int R, int ROWS, int NT>
+template <int R, int ROWS, int NT, int MAXC = (ROWS > 384 ? 8 : 16)>
 int launch_bcd_tc_cfg(const BcdBatch& b, cudaStream_t st) {
   const int need = (b.M + ROWS - 1) / ROWS;
   int csize = 1;
   while (csize < need) csize *= 2;
+  if (csize > MAXC) return fail(LRFB_E_UNSUPPORTED, "bcd_tc: %d rows need a cluster of %d > %d", b.M, csize, MAXC);
   const int rows_per_cta = (b.M + csize - 1) / csize;
-  auto kern = bcd_tc_kernel<R, ROWS, NT>;
+  auto kern = bcd_tc_kernel<R, ROWS, NT, MAXC>;
   const size_t smem = sizeof(TcSmem<R, ROWS, NT>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail((int)e, "bcd_tc smem attribute: %s", cudaGetErrorString(e));
@@ -369,6 +370,7 @@ template <int R>
 int launch_bcd_tc(const BcdBatch& b, cudaStream_t st) {
   if (tc_variant() == 1 || (tc_variant() == 2 && R <= 2)) return launch_bcd_tc_cfg<R, 384, 192>(b, st);
   if (tc_variant() == 3 || (tc_variant() == 4 && R == 4)) return launch_bcd_tc_cfg<R, 768, 256>(b, st);
+  if (b.M > 8 * kTcRows) return launch_bcd_tc_cfg<R, 768, 384, 16>(b, st);  // clusters of 16: up to 12 288 rows resident
   return launch_bcd_tc_cfg<R, 768, 384>(b, st);
 }
 bool tc_enabled() {
@@ -411,12 +413,22 @@ bool resident_ok(int N, int R, int M) {
 #endif
 }
 
+// the tensor-core sweeps kernel additionally runs 768-row CTAs in (non-portable) clusters of 16
+bool tc_resident_ok(int N, int R, int M, bool u8_range) {
+#ifdef LRFB_SIM
+  (void)N, (void)R, (void)M, (void)u8_range;
+  return false;
+#else
+  return u8_range && tc_enabled() && N == 64 && R <= 4 && !bmm_native(N, M, R) && M <= 16 * kTcRows;
+#endif
+}
+
 // `counter`: 4 bytes of device memory private to this call (the tensor-core kernel hands out matrices dynamically)
 int run_bcd(const BcdBatch& b0, int N, int R, float* bwork, cudaStream_t st, int* counter) {
   BcdBatch b = b0;
   b.work_counter = counter;
 #ifndef LRFB_SIM
-  if (resident_ok(N, R, b.M) && b.x_u8_range && tc_enabled() && b.M <= 8 * kTcRows) {
+  if (tc_resident_ok(N, R, b.M, b.x_u8_range != 0)) {
     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(int), st);
     if (e != cudaSuccess) return fail((int)e, "work counter reset: %s", cudaGetErrorString(e));
     switch (R) {
@@ -747,7 +759,9 @@ LRFB_EXPORT int32_t lrfb_qmf_encode(const lrfb_qmf_config* cfg, int32_t batch, c
   bool overlap = false;
 #ifndef LRFB_SIM
   overlap = L.n_planes == 3 && !(dbg && dbg->stop_after) && cfg->num_iters > 0 && !dev_getenv("LRFB_NO_OVERLAP");
-  for (int pl = 0; pl < L.n_planes && overlap; ++pl) overlap = resident_ok(L.cols, L.rank[pl], L.rows[pl]);
+  for (int pl = 0; pl < L.n_planes && overlap; ++pl)
+    overlap = resident_ok(L.cols, L.rank[pl], L.rows[pl]) ||
+              tc_resident_ok(L.cols, L.rank[pl], L.rows[pl], cfg->input_dtype == LRFB_U8);
   SideStream* side = overlap ? side_stream() : nullptr;
   SideUnlock side_guard{side};
   overlap = overlap && side;

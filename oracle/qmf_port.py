@@ -256,7 +256,7 @@ def decode_tensor(blob: bytes) -> torch.Tensor:
     if "num_fibers" in meta:
         return decode_matrix(blob)
     arr = np.frombuffer(zlib.decompress(body), dtype=np.dtype(meta["dtype"])).reshape(meta["shape"])
-    return torch.from_numpy(arr)
+    return torch.from_numpy(arr.copy())
 
 
 def _triple(v, halve):

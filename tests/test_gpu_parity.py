@@ -403,6 +403,6 @@ def test_patch_false_branches(manifest, name):
     assert torch.equal(dec, port.qmf_decode(blob))
     psnr = port.psnr(img, dec)
     print(f"\n[patch=False] {name}: bytes {len(blob)} vs {e['bytes']}, psnr {psnr:.4f} vs {e['psnr']:.4f}")
-    assert abs(psnr - e["psnr"]) <= 0.15 and abs(len(blob) - e["bytes"]) <= 0.03 * e["bytes"]
+    assert abs(psnr - e["psnr"]) <= 0.01 and abs(len(blob) - e["bytes"]) <= 0.01 * e["bytes"]
     meta = lrf_b200.bytes_to_dict(lrf_b200.separate_bytes(blob, 2)[0])
     assert meta == lrf_b200.bytes_to_dict(lrf_b200.separate_bytes(ref_blob, 2)[0])
