@@ -22,6 +22,7 @@
 #include "decode.cuh"
 #include "eig.cuh"
 #include "frontend.cuh"
+#include "frontgram.cuh"
 #include "gram.cuh"
 #include "gram_i8.cuh"
 #include "lrfb_common.cuh"
@@ -466,7 +467,7 @@ int factorize_batch(const float* x, int n_mat, int M, int N, int R, float lo, fl
                     float* v, int8_t* uq, int8_t* vq, long long q_stride, const float* init_u,
                     const float* init_v, const int32_t* sign_flip, double* gram, double* evec, double* sigma,
                     unsigned char* scratch, int stop_after_init, cudaStream_t st, int phase = 0,
-                    bool x_in_u8_range = false) {
+                    bool x_in_u8_range = false, bool gram_done = false) {
   // phase 0: init + sweeps, 1: init only, 2: sweeps only (after a phase-1 call with the same arguments)
   int rc;
   const bool injected = init_u && init_v;
@@ -487,11 +488,11 @@ int factorize_batch(const float* x, int n_mat, int M, int N, int R, float lo, fl
     if ((rc = dev_copy(u, init_u, (size_t)n_mat * M * R * 4, st))) return fail(rc, "copy init u");
     if ((rc = dev_copy(v, init_v, (size_t)n_mat * N * R * 4, st))) return fail(rc, "copy init v");
   } else {
-    // G = X^T X in f64
+    // G = X^T X in f64 (unless the fused front end has produced it already)
     const int nb = ((N + 3) / 4);
     const int nblocks = nb * (nb + 1) / 2;
     double* gout = split > 1 ? gram_part : gram;
-    for (int m0 = 0; m0 < n_mat; m0 += 65535) {
+    for (int m0 = 0; m0 < n_mat && !gram_done; m0 += 65535) {
       int cnt = std::min(65535, n_mat - m0);
       const float* xx = x + (size_t)m0 * M * N;
       double* go = gout + (size_t)m0 * split * N * N;
@@ -630,6 +631,18 @@ bool fused8_geometry(const lrfb_qmf_config* cfg, const Geometry& g, const void* 
          f.g[0].hp == f.H && f.g[1].hp * 2 == f.H && g.lay.n_planes == 3;
 }
 
+// front end fused with the luma Gram (frontgram.cuh): additionally W % 256 == 0, N = 64, no Gram row split (large batch)
+bool frontgram_ok(const lrfb_qmf_config* cfg, const Geometry& g, int batch) {
+#ifdef LRFB_SIM
+  (void)cfg, (void)g, (void)batch;
+  return false;
+#else
+  static const bool off = dev_getenv("LRFB_NO_FRONTGRAM") != nullptr;
+  return !off && cfg->width % 256 == 0 && g.lay.cols == 64 && g.lay.rows[0] <= 60000 &&
+         FactorWs::gram_split(batch, g.lay.rows[0]) == 1;
+#endif
+}
+
 // planes: bit 0 = plane 0 (luma / RGB), bit 1 = planes 1 and 2 (chroma)
 int run_frontend(const lrfb_qmf_config* cfg, const Geometry& g, int batch, const void* d_images,
                  float* const* xs, cudaStream_t st, int planes = 3) {
@@ -741,6 +754,7 @@ LRFB_EXPORT int32_t lrfb_qmf_encode(const lrfb_qmf_config* cfg, int32_t batch, c
   float* xs[3];
   for (int pl = 0; pl < 3; ++pl) xs[pl] = reinterpret_cast<float*>(ws + m.x[pl]);
   const lrfb_qmf_layout& L = g.lay;
+  bool luma_gram_done = false;
   auto run_plane = [&](int pl, int phase, cudaStream_t s) {
     return factorize_batch(xs[pl], batch, L.rows[pl], L.cols, L.rank[pl], cfg->bound_lo, cfg->bound_hi,
                            cfg->num_iters, reinterpret_cast<float*>(ws + m.u[pl]),
@@ -749,7 +763,8 @@ LRFB_EXPORT int32_t lrfb_qmf_encode(const lrfb_qmf_config* cfg, int32_t batch, c
                            dbg ? dbg->d_init_v[pl] : nullptr, dbg ? dbg->d_sign_flip[pl] : nullptr,
                            reinterpret_cast<double*>(ws + m.gram[pl]), reinterpret_cast<double*>(ws + m.evec[pl]),
                            reinterpret_cast<double*>(ws + m.sigma[pl]), ws + m.total_bytes,
-                           dbg && dbg->stop_after == 2, s, phase, cfg->input_dtype == LRFB_U8);
+                           dbg && dbg->stop_after == 2, s, phase, cfg->input_dtype == LRFB_U8,
+                           pl == 0 && luma_gram_done);
   };
   // The planes are independent.  When every plane runs the shared-memory-resident sweeps (no shared scratch),
   // the chroma work goes to a low-priority helper stream: the luma sweeps occupy 15 clusters x 8 SMs, the
@@ -772,7 +787,18 @@ LRFB_EXPORT int32_t lrfb_qmf_encode(const lrfb_qmf_config* cfg, int32_t batch, c
       // Three initialisation chains (Gram + eigen-solver: the latter latency-bound) run side by side; then the luma
       // sweeps take their 15 clusters x 8 SMs and the chroma sweeps (Cb, then Cr) the SMs that leaves free.
       if (fused8_geometry(cfg, g, d_images)) {  // the image is read once; the chroma chains fork after it
-        if ((rc = run_frontend(cfg, g, batch, d_images, xs, st, 3))) return rc;
+        if (frontgram_ok(cfg, g, batch) && !(dbg && dbg->d_init_u[0] && dbg->d_init_v[0])) {
+          // front end + luma Gram in one pass: X_y is written but never read back for its Gram
+          const size_t fsmem = sizeof(FrontGramSmem) + 1024;
+          cudaError_t e = cudaFuncSetAttribute(frontgram8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+          if (e != cudaSuccess) return fail((int)e, "frontgram smem attribute: %s", cudaGetErrorString(e));
+          frontgram8_kernel<<<dim3((unsigned)batch), dim3(kFgThreads), fsmem, st>>>(
+              (const unsigned char*)d_images, xs[0], xs[1], xs[2], reinterpret_cast<double*>(ws + m.gram[0]), g.fp);
+          if ((rc = check_launch("frontgram8_kernel"))) return rc;
+          luma_gram_done = true;
+        } else if ((rc = run_frontend(cfg, g, batch, d_images, xs, st, 3))) {
+          return rc;
+        }
         cudaEventRecord(side->fork, st);
         cudaStreamWaitEvent(side->stream, side->fork, 0);
       } else {

@@ -406,3 +406,25 @@ def test_patch_false_branches(manifest, name):
     assert abs(psnr - e["psnr"]) <= 0.01 and abs(len(blob) - e["bytes"]) <= 0.01 * e["bytes"]
     meta = lrf_b200.bytes_to_dict(lrf_b200.separate_bytes(blob, 2)[0])
     assert meta == lrf_b200.bytes_to_dict(lrf_b200.separate_bytes(ref_blob, 2)[0])
+
+
+def test_fused_frontend_gram_path_equals_separate_kernels():
+    """Large batches of W % 256 == 0 images take the fused front-end + luma-Gram kernel (frontgram.cuh); single images
+    take the separate front-end and Gram kernels.  Both must give the same records, and the patch matrices the fused
+    kernel leaves in the workspace must be the oracle's, bit for bit."""
+    import lrf_b200
+    from lrf_b200 import compression
+
+    H, W, B = 64, 256, 640
+    base = torch.stack([port.s_nat(6000 + i, H, W) for i in range(8)])
+    imgs = base[torch.arange(B) % 8].contiguous().cuda()
+    cfg, lay = compression.resolve_plan(H, W, None, 7, "YCbCr", (0.5, 0.5), (8, 8), (-16, 15), 10)
+    plan = compression.EncodePlan(cfg, lay, B, imgs.device)
+    rec = plan.run(imgs).cpu()
+    for i in range(8):
+        single, _, _ = lrf_b200.qmf_encode_batch(base[i:i + 1], return_records=True, **README_KW)
+        assert torch.equal(single.cpu()[0], rec[i]), i
+        assert torch.equal(rec[i], rec[B - 8 + i])
+        xs = exact.frontend(base[i].numpy())
+        for pl in range(3):
+            assert np.array_equal(plan.view("x", pl)[i].cpu().numpy(), xs[pl]), (i, pl)
