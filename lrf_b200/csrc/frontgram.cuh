@@ -143,6 +143,7 @@ frontgram8_kernel(const unsigned char* __restrict__ images, float* __restrict__ 
         float* s_cr = sm.xcr[grp];
         asm volatile("bar.sync %0, 256;" ::"r"(1 + grp) : "memory");  // the group's previous write-out is done with s_*
         float sb[4] = {0.0f, 0.0f, 0.0f, 0.0f}, sr[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        unsigned sl[4][4];  // [slice][word]: the 16 bytes of this strip's core-matrix row per slice
 #pragma unroll
         for (int dy = 0; dy < 2; ++dy) {
           const int ly = 2 * cy + dy;
@@ -164,25 +165,27 @@ frontgram8_kernel(const unsigned char* __restrict__ images, float* __restrict__ 
           float* d = &s_lum[((ly >> 3) * 32 + wp) * kTilePatchStride + (ly & 7) * 8];
           *reinterpret_cast<float4*>(d) = make_float4(lum[0], lum[1], lum[2], lum[3]);
           *reinterpret_cast<float4*>(d + 4) = make_float4(lum[4], lum[5], lum[6], lum[7]);
-          // Q8.24 byte slices of the 8 values into the staging: tile row m, columns n = (ly & 7) * 8 .. + 7
+          // Q8.24 byte slices of the 8 values: tile row m, columns n = (ly & 7) * 8 .. + 7.  The strip's two image rows
+          // are the two halves of one 16-byte core-matrix row, stored together below (conflict-free 16-byte stores).
           unsigned w[8];
 #pragma unroll
           for (int k = 0; k < 8; ++k) w[k] = __float2uint_rz(lum[k] * 16777216.0f);
-          const int m = (ly >> 3) * 32 + wp, n0 = (ly & 7) * 8;
-          const unsigned off = (n0 >> 4) * kFgSbo + (m >> 3) * 128 + (m & 7) * 16 + (n0 & 15);
-          unsigned sl[4][2];  // [slice][half]: values 4h .. 4h+3 packed into one 32-bit word per slice
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
+          for (int h = 0; h < 2; ++h) {  // values 4h .. 4h+3 packed into one 32-bit word per slice
             const unsigned a = __byte_perm(w[4 * h], w[4 * h + 1], 0x5140), b = __byte_perm(w[4 * h], w[4 * h + 1], 0x7362);
             const unsigned c = __byte_perm(w[4 * h + 2], w[4 * h + 3], 0x5140), e = __byte_perm(w[4 * h + 2], w[4 * h + 3], 0x7362);
-            sl[0][h] = __byte_perm(b, e, 0x7632);  // bits 31..24
-            sl[1][h] = __byte_perm(b, e, 0x5410);  // bits 23..16
-            sl[2][h] = __byte_perm(a, c, 0x7632);  // bits 15..8
-            sl[3][h] = __byte_perm(a, c, 0x5410);  // bits 7..0
+            sl[0][2 * dy + h] = __byte_perm(b, e, 0x7632);  // bits 31..24
+            sl[1][2 * dy + h] = __byte_perm(b, e, 0x5410);  // bits 23..16
+            sl[2][2 * dy + h] = __byte_perm(a, c, 0x7632);  // bits 15..8
+            sl[3][2 * dy + h] = __byte_perm(a, c, 0x5410);  // bits 7..0
           }
+        }
+        {
+          const int ly = 2 * cy, m = (ly >> 3) * 32 + wp, n0 = (ly & 7) * 8;  // n0 is a multiple of 16
+          const unsigned off = (n0 >> 4) * kFgSbo + (m >> 3) * 128 + (m & 7) * 16;
 #pragma unroll
           for (int a = 0; a < 4; ++a)
-            *reinterpret_cast<uint2*>(st + a * kFgSliceBytes + off) = make_uint2(sl[a][0], sl[a][1]);
+            *reinterpret_cast<uint4*>(st + a * kFgSliceBytes + off) = make_uint4(sl[a][0], sl[a][1], sl[a][2], sl[a][3]);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (MMA)
         mbar_arrive(&sm.full[s]);
