@@ -224,8 +224,10 @@ int launch_bcd_fast(const BcdBatch& b, cudaStream_t st) {
     const char* e = dev_getenv("LRFB_BCD_VARIANT");
     variant = e ? atoi(e) : 1;
   }
+#ifdef LRFB_DEV  // alternative shapes are instantiated in development builds only
   if (variant == 0) return launch_bcd_cfg<R, 128, 64>(b, st);
   if (variant == 2) return launch_bcd_cfg<R, 64, 64>(b, st);
+#endif
   return launch_bcd_cfg<R, 128, 128>(b, st);
 }
 
@@ -369,8 +371,10 @@ int tc_variant() {
 }
 template <int R>
 int launch_bcd_tc(const BcdBatch& b, cudaStream_t st) {
+#ifdef LRFB_DEV  // alternative shapes are instantiated in development builds only
   if (tc_variant() == 1 || (tc_variant() == 2 && R <= 2)) return launch_bcd_tc_cfg<R, 384, 192>(b, st);
   if (tc_variant() == 3 || (tc_variant() == 4 && R == 4)) return launch_bcd_tc_cfg<R, 768, 256>(b, st);
+#endif
   if (b.M > 8 * kTcRows) return launch_bcd_tc_cfg<R, 768, 384, 16>(b, st);  // clusters of 16: up to 12 288 rows resident
   return launch_bcd_tc_cfg<R, 768, 384>(b, st);
 }
@@ -395,9 +399,11 @@ int resident_variant() {
 
 template <int R>
 int launch_bcd_resident(const BcdBatch& b, cudaStream_t st) {
-  if (resident_variant() == 0) return launch_bcd_resident_cfg<R, 768, 384, 8>(b, st);
+#ifdef LRFB_DEV  // alternative shapes are instantiated in development builds only
   if (resident_variant() == 2) return launch_bcd_resident_cfg<R, 768, 256, 8>(b, st);
-  return launch_bcd_resident_cfg<R, 384, 192, 16>(b, st);
+  if (resident_variant() == 1) return launch_bcd_resident_cfg<R, 384, 192, 16>(b, st);
+#endif
+  return launch_bcd_resident_cfg<R, 768, 384, 8>(b, st);
 }
 
 bool resident_ok(int N, int R, int M) {
