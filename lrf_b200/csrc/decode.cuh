@@ -237,77 +237,86 @@ qmf_decode8x2_kernel(const int8_t* __restrict__ factors, unsigned char* __restri
   const float t[3][3] = {{1.0f, 0.0f, 1.40200f}, {1.0f, -0.344136f, -0.714136f}, {1.0f, 1.77200f, 0.0f}};
   const size_t hw = (size_t)P.H * P.W;
   const int segs = P.W / 8;
-  const long long items = (long long)(P.H / 2) * segs;
+  const long long items = (long long)(P.H / 8) * segs;  // one item = one luma patch (8 rows x 8 pixels)
   const PlaneGeom gy = P.g[0], gc = P.g[1];
   for (int im = blockIdx.y; im < P.n_img; im += gridDim.y) {
     const int8_t* rec = factors + (size_t)im * P.record_bytes;
     unsigned char* o = out + (size_t)im * 3 * hw;
     for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items;
          it += (long long)gridDim.x * blockDim.x) {
-      const int cy = (int)(it / segs), sg = (int)(it - (long long)cy * segs);
-      // ---- chroma: 4 columns 4*sg .. 4*sg+3 of chroma row cy, both planes ----
-      int pc[2][4];
-      {
-        const int cx0 = 4 * sg, m = (cy >> 3) * gc.nbw + (cx0 >> 3), col = (cy & 7) * 8 + (cx0 & 7);
-#pragma unroll
-        for (int pl = 0; pl < 2; ++pl) {
-          const int8_t* u = rec + P.u_off[1 + pl];
-          const int8_t* v = rec + P.v_off[1 + pl];
-          unsigned uw = 0, vr[4] = {0, 0, 0, 0}, w[4];
-#pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            if (r < P.rank[1 + pl]) {
-              uw |= (unsigned)(unsigned char)u[(size_t)r * gc.rows + m] << (8 * r);
-              vr[r] = *reinterpret_cast<const unsigned*>(v + (size_t)r * 64 + col);
-            }
-          }
-          transpose4x4_bytes(vr[0], vr[1], vr[2], vr[3], w);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) pc[pl][j] = __dp4a((int)w[j], (int)uw, 0);
-        }
-      }
-      float cb[4], cr[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) cb[j] = __fadd_rn((float)pc[0][j], -128.0f), cr[j] = __fadd_rn((float)pc[1][j], -128.0f);
-      // ---- luma: rows 2cy and 2cy+1 lie in the same patch row, so they share the U word ----
-      const int y0 = 2 * cy, m = (y0 >> 3) * gy.nbw + sg;
+      const int pr = (int)(it / segs), sg = (int)(it - (long long)pr * segs);
+      // The 8 rows of the patch share the luma U word; their 4 chroma rows lie in one chroma patch and share its U words:
+      // the byte gathers from the fiber-major factors and the index arithmetic are paid once per 64 pixels.
+      const int m = pr * gy.nbw + sg;
       const int8_t* u = rec + P.u_off[0];
       const int8_t* v = rec + P.v_off[0];
       unsigned uw = 0;
 #pragma unroll
       for (int r = 0; r < 4; ++r)
         if (r < P.rank[0]) uw |= (unsigned)(unsigned char)u[(size_t)r * gy.rows + m] << (8 * r);
+      const int cx0 = 4 * sg, mc = (pr >> 1) * gc.nbw + (cx0 >> 3);
+      unsigned uwc[2] = {0, 0};
 #pragma unroll
-      for (int dy = 0; dy < 2; ++dy) {
-        const int y = y0 + dy, col = (y & 7) * 8;
-        uint2 vr[4];
+      for (int pl = 0; pl < 2; ++pl)
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          vr[r] = make_uint2(0u, 0u);
-          if (r < P.rank[0]) vr[r] = *reinterpret_cast<const uint2*>(v + (size_t)r * 64 + col);
-        }
-        unsigned wl[4], wh[4];
-        transpose4x4_bytes(vr[0].x, vr[1].x, vr[2].x, vr[3].x, wl);
-        transpose4x4_bytes(vr[0].y, vr[1].y, vr[2].y, vr[3].y, wh);
-        unsigned px[3][8];
+        for (int r = 0; r < 4; ++r)
+          if (r < P.rank[1 + pl])
+            uwc[pl] |= (unsigned)(unsigned char)rec[P.u_off[1 + pl] + (size_t)r * gc.rows + mc] << (8 * r);
+#pragma unroll 1
+      for (int q = 0; q < 4; ++q) {
+        const int cy = 4 * pr + q;
+        // ---- chroma: 4 columns 4*sg .. 4*sg+3 of chroma row cy, both planes ----
+        int pc[2][4];
+        {
+          const int col = (cy & 7) * 8 + (cx0 & 7);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float yv = (float)__dp4a((int)(j < 4 ? wl[j & 3] : wh[j & 3]), (int)uw, 0);
+          for (int pl = 0; pl < 2; ++pl) {
+            const int8_t* vc = rec + P.v_off[1 + pl];
+            unsigned vr[4] = {0, 0, 0, 0}, w[4];
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            float acc = __fmul_rn(t[c][0], yv);
-            acc = __fmaf_rn(t[c][1], cb[j >> 1], acc);
-            acc = __fmaf_rn(t[c][2], cr[j >> 1], acc);
-            acc = fminf(fmaxf(acc, 0.0f), 255.0f);
-            px[c][j] = __float_as_uint(__fadd_rz(acc, 8388608.0f));  // pixel value in the low byte
+            for (int r = 0; r < 4; ++r)
+              if (r < P.rank[1 + pl]) vr[r] = *reinterpret_cast<const unsigned*>(vc + (size_t)r * 64 + col);
+            transpose4x4_bytes(vr[0], vr[1], vr[2], vr[3], w);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pc[pl][j] = __dp4a((int)w[j], (int)uwc[pl], 0);
           }
         }
-        const size_t off = (size_t)y * P.W + (size_t)sg * 8;
+        float cb[4], cr[4];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {  // low bytes of 4 words -> one word: 3 PRMT
-          const unsigned lo = __byte_perm(__byte_perm(px[c][0], px[c][1], 0x0040), __byte_perm(px[c][2], px[c][3], 0x0040), 0x5410);
-          const unsigned hi = __byte_perm(__byte_perm(px[c][4], px[c][5], 0x0040), __byte_perm(px[c][6], px[c][7], 0x0040), 0x5410);
-          *reinterpret_cast<uint2*>(o + c * hw + off) = make_uint2(lo, hi);
+        for (int j = 0; j < 4; ++j) cb[j] = __fadd_rn((float)pc[0][j], -128.0f), cr[j] = __fadd_rn((float)pc[1][j], -128.0f);
+        // ---- luma rows 2cy and 2cy+1 ----
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+          const int y = 2 * cy + dy, col = (y & 7) * 8;
+          uint2 vr[4];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            vr[r] = make_uint2(0u, 0u);
+            if (r < P.rank[0]) vr[r] = *reinterpret_cast<const uint2*>(v + (size_t)r * 64 + col);
+          }
+          unsigned wl[4], wh[4];
+          transpose4x4_bytes(vr[0].x, vr[1].x, vr[2].x, vr[3].x, wl);
+          transpose4x4_bytes(vr[0].y, vr[1].y, vr[2].y, vr[3].y, wh);
+          unsigned px[3][8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float yv = (float)__dp4a((int)(j < 4 ? wl[j & 3] : wh[j & 3]), (int)uw, 0);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              float acc = __fmul_rn(t[c][0], yv);
+              acc = __fmaf_rn(t[c][1], cb[j >> 1], acc);
+              acc = __fmaf_rn(t[c][2], cr[j >> 1], acc);
+              acc = fminf(fmaxf(acc, 0.0f), 255.0f);
+              px[c][j] = __float_as_uint(__fadd_rz(acc, 8388608.0f));  // pixel value in the low byte
+            }
+          }
+          const size_t off = (size_t)y * P.W + (size_t)sg * 8;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {  // low bytes of 4 words -> one word: 3 PRMT
+            const unsigned lo = __byte_perm(__byte_perm(px[c][0], px[c][1], 0x0040), __byte_perm(px[c][2], px[c][3], 0x0040), 0x5410);
+            const unsigned hi = __byte_perm(__byte_perm(px[c][4], px[c][5], 0x0040), __byte_perm(px[c][6], px[c][7], 0x0040), 0x5410);
+            *reinterpret_cast<uint2*>(o + c * hw + off) = make_uint2(lo, hi);
+          }
         }
       }
     }

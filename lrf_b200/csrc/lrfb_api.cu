@@ -950,7 +950,7 @@ LRFB_EXPORT int32_t lrfb_qmf_decode(const lrfb_qmf_config* cfg, int32_t batch, c
 #ifndef LRFB_SIM
     if (fused8_geometry(cfg, g, d_images) && g.lay.rank[0] <= 4 && g.lay.rank[1] <= 4 && g.lay.rank[2] <= 4 &&
         !g_decode_v1.load(std::memory_order_relaxed)) {
-      dim3 grid2((unsigned)std::min<long long>((items / 2 + 255) / 256, 4096), std::min(batch, 65535));
+      dim3 grid2((unsigned)std::min<long long>((items / 8 + 255) / 256, 4096), std::min(batch, 65535));  // one thread per luma patch
       LRFB_LAUNCH(qmf_decode8x2_kernel, grid2, dim3(256), 0, (cudaStream_t)(uintptr_t)stream, d_factors, d_images, P);
       return check_launch("qmf_decode8x2_kernel");
     }
