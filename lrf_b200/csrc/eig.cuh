@@ -308,9 +308,11 @@ eig_topr_kernel(const double* __restrict__ Gin, int Nrt, int R, double* __restri
     for (int i = lane; i < 4 * N; i += 32) g4s[i] = A[i];
   __syncwarp();
 
-  // ---- 1. tridiagonalisation -------------------------------------------------------------------
+  // ---- 1. tridiagonalisation, in two stages (see eig64_topr_kernel: the e_0-preserving reduction is the Lanczos
+  //         process from e_0; natural-image spectra converge long before the matrix is fully reduced) ----
+  auto reduce = [&](int k_begin, int k_end) {
 #pragma unroll 1
-  for (int k = 0; k < N - 2; ++k) {
+  for (int k = k_begin; k < k_end; ++k) {
     const double* rowk = A + k * N;  // x = A[k][k+1..] (= column k by symmetry)
     const double alpha0 = rowk[k + 1];
     double part = 0.0;
@@ -364,31 +366,22 @@ eig_topr_kernel(const double* __restrict__ Gin, int Nrt, int R, double* __restri
     for (int c = k + 1 + lane; c < N; c += 32) A[k * N + c] = vv[c];  // keep reflector k in row k
     __syncwarp();
   }
-  if (lane == 0) {
-    if (N >= 2) {
-      d[N - 2] = A[(N - 2) * N + (N - 2)];
-      e[N - 2] = A[(N - 2) * N + (N - 1)];
-      tau[N - 2] = 0.0;
-    }
-    d[N - 1] = A[(N - 1) * N + (N - 1)];
-    e[N - 1] = 0.0;
-    tau[N - 1] = 0.0;
-  }
-  __syncwarp();
-
+  };
+  double tnorm_out = 0.0;
+  auto solve = [&](int L) {
   // ---- 2. R largest eigenvalues by multisection ------------------------------------------------
   double glo = d[0], ghi = d[0], maxe2 = 0.0;
 #pragma unroll 1
-  for (int i = 0; i < N; ++i) {  // Gershgorin bounds, redundantly per lane
-    double r = (i > 0 ? fabs(e[i - 1]) : 0.0) + (i < N - 1 ? fabs(e[i]) : 0.0);
+  for (int i = 0; i < L; ++i) {  // Gershgorin bounds, redundantly per lane
+    double r = (i > 0 ? fabs(e[i - 1]) : 0.0) + (i < L - 1 ? fabs(e[i]) : 0.0);
     glo = fmin(glo, d[i] - r);
     ghi = fmax(ghi, d[i] + r);
-    maxe2 = fmax(maxe2, e[i] * e[i]);
+    if (i < L - 1) maxe2 = fmax(maxe2, e[i] * e[i]);
   }
   const double tnorm = fmax(fabs(glo), fabs(ghi));
   const double pivmin = 1e-290 * fmax(1.0, maxe2);
-  glo -= 2.3e-16 * tnorm * N + pivmin;
-  ghi += 2.3e-16 * tnorm * N + pivmin;
+  glo -= 2.3e-16 * tnorm * L + pivmin;
+  ghi += 2.3e-16 * tnorm * L + pivmin;
   int ppe = 32;  // probes per eigenvalue: largest power of two with (32 / ppe) >= min(R, 32)
   while (ppe > 1 && 32 / ppe < min(R, 32)) ppe >>= 1;
   const int groups = 32 / ppe;
@@ -401,13 +394,13 @@ eig_topr_kernel(const double* __restrict__ Gin, int Nrt, int R, double* __restri
     const int grp = lane / ppe, pr = lane % ppe;
     const int r = r0 + grp;
     const bool active = r < R;
-    const int idx = N - 1 - r;  // ascending index of the r-th largest
+    const int idx = L - 1 - r;  // ascending index of the r-th largest
     double lo = glo, hi = ghi;
 #pragma unroll 1
     for (int round = 0; round < rounds; ++round) {
       const double step = (hi - lo) / (double)(ppe + 1);
       const double x = lo + step * (double)(pr + 1);
-      const int cnt = active ? sturm_count(d, e, N, x, pivmin) : 0;
+      const int cnt = active ? sturm_count(d, e, L, x, pivmin) : 0;
       const unsigned ballot = __ballot_sync(0xffffffffu, active && cnt > idx);
       const unsigned bits = (ppe == 32) ? ballot : ((ballot >> (grp * ppe)) & ((1u << ppe) - 1u));
       const int f = bits ? (__ffs((int)bits) - 1) : ppe;  // first probe with count > idx
@@ -419,9 +412,12 @@ eig_topr_kernel(const double* __restrict__ Gin, int Nrt, int R, double* __restri
   }
   __syncwarp();
 
-  // ---- 3. eigenvectors of the tridiagonal ---------------------------------------------------------
+  // ---- 3. eigenvectors of the tridiagonal (leading L x L block) ---------------------------------------
   for (int r = lane; r < R; r += 32)
-    tridiag_inverse_iteration(d, e, N, lam[r], tnorm, z + r * N, lu + r * 5 * N, r);
+  {
+    tridiag_inverse_iteration(d, e, L, lam[r], tnorm, z + r * N, lu + r * 5 * N, r);
+    for (int i = L; i < N; ++i) z[r * N + i] = 0.0;
+  }
   __syncwarp();
   if (lane == 0) {  // modified Gram–Schmidt in eigenvalue order (only matters for near-multiple eigenvalues)
     for (int r = 0; r < R; ++r) {
@@ -458,11 +454,48 @@ eig_topr_kernel(const double* __restrict__ Gin, int Nrt, int R, double* __restri
   }
   __syncwarp();
 
+  };
+  int n_refl = N - 2;  // reflectors formed
+  {
+    const int k_fast = min(N - 2, max(23, 4 * R + 15));
+    bool done = false;
+    if (k_fast < N - 2) {
+      reduce(0, k_fast);
+      double cn2 = 0.0;  // coupling of row k_fast to the unreduced part
+      for (int c = k_fast + 1 + lane; c < N; c += 32) cn2 = fma(A[k_fast * N + c], A[k_fast * N + c], cn2);
+      cn2 = warp_sum(cn2);
+      if (lane == 0) d[k_fast] = A[k_fast * N + k_fast], e[k_fast] = 0.0;
+      __syncwarp();
+      solve(k_fast + 1);
+      done = true;
+      const double lam0 = fmax(lam[0], 0.0);
+      for (int r = 0; r < R; ++r)
+        if (lam[r] > 1e-14 * lam0) done = done && sqrt(cn2) * fabs(z[r * N + k_fast]) <= 1e-15 * lam0;
+      __syncwarp();
+      if (done) n_refl = k_fast;
+    }
+    if (!done) {
+      reduce(k_fast < N - 2 ? k_fast : 0, N - 2);
+  if (lane == 0) {
+    if (N >= 2) {
+      d[N - 2] = A[(N - 2) * N + (N - 2)];
+      e[N - 2] = A[(N - 2) * N + (N - 1)];
+      tau[N - 2] = 0.0;
+    }
+    d[N - 1] = A[(N - 1) * N + (N - 1)];
+    e[N - 1] = 0.0;
+    tau[N - 1] = 0.0;
+  }
+  __syncwarp();
+
+      solve(N);
+    }
+  }
   // ---- 4. back-transform: z <- H_0 H_1 ... H_{N-3} z, four vectors at a time ----------------------
   for (int r0 = 0; r0 < R; r0 += 4) {
     const int nv = min(4, R - r0);
 #pragma unroll 1
-    for (int k = N - 3; k >= 0; --k) {
+    for (int k = min(N - 3, n_refl - 1); k >= 0; --k) {
       const double tk = tau[k];
       if (tk == 0.0) continue;
       const double* hk = A + k * N;  // reflector k: hk[k+1] = 1, hk[k+2..]

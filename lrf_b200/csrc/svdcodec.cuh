@@ -32,26 +32,42 @@ svd_project_kernel(const float* __restrict__ X, long long x_stride, int M, int N
   for (int r0 = blockIdx.x * kProjRows; r0 < M; r0 += gridDim.x * kProjRows) {
     const int valid = min(kProjRows, M - r0);
     __syncthreads();
-    for (int row = 0; row < valid; ++row)
-      for (int c = threadIdx.x; c < N; c += blockDim.x) xt[row * XS + c] = x[(size_t)(r0 + row) * N + c];
+    for (int i = threadIdx.x; i < valid * N; i += blockDim.x) {  // coalesced: consecutive threads, consecutive elements
+      const int row = i / N, c = i - row * N;
+      xt[row * XS + c] = x[(size_t)r0 * N + i];
+    }
     __syncthreads();
     const int m = threadIdx.x;
     if (m < valid) {
-      for (int c0 = 0; c0 < R; c0 += 4) {
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int k = 0; k < N; ++k) {
-          const double xv = (double)xt[m * XS + k];
+      for (int c0 = 0; c0 < R; c0 += 16) {  // up to 16 columns per pass over the row
+        double acc[16];
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (c0 + j < R) acc[j] = fma(xv, ev[k * R + c0 + j], acc[j]);
+        for (int j = 0; j < 16; ++j) acc[j] = 0.0;
+        const int nc = min(16, R - c0);
+        if (nc == 16) {
+#pragma unroll 2
+          for (int k = 0; k < N; ++k) {
+            const double xv = (double)xt[m * XS + k];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] = fma(xv, ev[k * R + c0 + j], acc[j]);
+          }
+        } else {
+#pragma unroll 2
+          for (int k = 0; k < N; ++k) {
+            const double xv = (double)xt[m * XS + k];
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j < nc) acc[j] = fma(xv, ev[k * R + c0 + j], acc[j]);
+          }
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 16; ++j) {
           const int r = c0 + j;
-          if (r >= R) break;
-          float val = 0.0f;
-          if (r < keep && sg[r] > 0.0) val = __fmul_rn((float)(acc[j] / sg[r]), __fsqrt_rn((float)sg[r]));
-          u[(size_t)(r0 + m) * R + r] = val;
+          if (j < nc) {
+            float val = 0.0f;
+            if (r < keep && sg[r] > 0.0) val = __fmul_rn((float)(acc[j] / sg[r]), __fsqrt_rn((float)sg[r]));
+            u[(size_t)(r0 + m) * R + r] = val;
+          }
         }
       }
     }
