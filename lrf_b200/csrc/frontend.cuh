@@ -145,6 +145,31 @@ frontend8_luma_kernel(const unsigned char* __restrict__ images, float* __restric
   }
 }
 
+// RGB planes (color_space="RGB": SVD codec, QMF on RGB), 8x8 patches, W % 8 == 0: one thread converts 8 consecutive
+// pixels of one patch row of one channel (8-byte load, two 16-byte stores); X[m][c*64 + py*8 + px].
+__global__ void __launch_bounds__(256)
+frontend8_rgb_kernel(const unsigned char* __restrict__ images, float* __restrict__ xout, FrontParams P) {
+  const PlaneGeom g = P.g[0];
+  const size_t hw = (size_t)P.H * P.W;
+  const int nbw = g.nbw;  // == W/8
+  const long long items = 3LL * g.hp * nbw;
+  for (int im = blockIdx.y; im < P.n_img; im += gridDim.y) {
+    const unsigned char* img = images + (size_t)im * 3 * hw;
+    float* x = xout + (size_t)im * g.rows * 192;
+    for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items;
+         it += (long long)gridDim.x * blockDim.x) {
+      const int wb = (int)(it % nbw);
+      const long long t = it / nbw;
+      const int c = (int)(t % 3), yy = (int)(t / 3);
+      const int y = reflect_idx(yy - g.top, g.h);
+      const uint2 v = *reinterpret_cast<const uint2*>(img + (size_t)c * hw + (size_t)y * P.W + (size_t)wb * 8);
+      float* dst = x + ((size_t)(yy >> 3) * nbw + wb) * 192 + c * 64 + (yy & 7) * 8;
+      *reinterpret_cast<float4*>(dst) = make_float4(byte_of(v.x, 0), byte_of(v.x, 1), byte_of(v.x, 2), byte_of(v.x, 3));
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(byte_of(v.y, 0), byte_of(v.y, 1), byte_of(v.y, 2), byte_of(v.y, 3));
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 frontend8_chroma_kernel(const unsigned char* __restrict__ images, float* __restrict__ xcb,
                         float* __restrict__ xcr, FrontParams P) {

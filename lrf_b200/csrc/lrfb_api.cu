@@ -25,6 +25,7 @@
 #include "frontgram.cuh"
 #include "gram.cuh"
 #include "gram_i8.cuh"
+#include "gram_u8.cuh"
 #include "lrfb_common.cuh"
 #include "svdcodec.cuh"
 
@@ -473,7 +474,7 @@ int factorize_batch(const float* x, int n_mat, int M, int N, int R, float lo, fl
                     float* v, int8_t* uq, int8_t* vq, long long q_stride, const float* init_u,
                     const float* init_v, const int32_t* sign_flip, double* gram, double* evec, double* sigma,
                     unsigned char* scratch, int stop_after_init, cudaStream_t st, int phase = 0,
-                    bool x_in_u8_range = false, bool gram_done = false) {
+                    bool x_in_u8_range = false, bool gram_done = false, bool x_integer_u8 = false) {
   // phase 0: init + sweeps, 1: init only, 2: sweeps only (after a phase-1 call with the same arguments)
   int rc;
   const bool injected = init_u && init_v;
@@ -508,7 +509,13 @@ int factorize_batch(const float* x, int n_mat, int M, int N, int R, float lo, fl
         const char* ev = dev_getenv("LRFB_GRAM_I8");
         use_i8 = ev ? atoi(ev) : 1;
       }
-      if (N == 64 && x_in_u8_range && use_i8 && (M + split - 1) / split <= 60000) {
+      if (N == kU8N && x_integer_u8 && use_i8 && (M + split - 1) / split <= 60000) {
+        // RGB planes of uint8 images: the bytes are the operands (one slice)
+        const size_t usmem = sizeof(GramU8Smem) + 1024;
+        cudaError_t e = cudaFuncSetAttribute(gram192_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)usmem);
+        if (e != cudaSuccess) return fail((int)e, "gram_u8 smem attribute: %s", cudaGetErrorString(e));
+        gram192_u8_kernel<<<dim3(split, cnt), dim3(kI8Threads), usmem, st>>>(xx, (long long)M * N, M, go, split);
+      } else if (N == 64 && x_in_u8_range && use_i8 && (M + split - 1) / split <= 60000) {
         // exact int8 tensor-core Gram (tcgen05): entries of X are in [0, 256)
         const size_t ismem = sizeof(GramI8Smem) + 1024;
         cudaError_t e = cudaFuncSetAttribute(gram64_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ismem);
@@ -674,6 +681,13 @@ int run_frontend(const lrfb_qmf_config* cfg, const Geometry& g, int batch, const
     }
     return 0;
   }
+  if (!g.fp.ycbcr && cfg->input_dtype == LRFB_U8 && g.fp.p == 8 && g.fp.q == 8 && g.fp.W % 8 == 0 &&
+      g.fp.g[0].wp == g.fp.W && ((uintptr_t)d_images % 8) == 0 && (planes & 1)) {
+    long long items = 3LL * g.fp.g[0].hp * g.fp.g[0].nbw;
+    dim3 grid((unsigned)std::min<long long>((items + 255) / 256, 8192), std::min(batch, 65535));
+    LRFB_LAUNCH(frontend8_rgb_kernel, grid, dim3(256), 0, st, (const unsigned char*)d_images, xs[0], g.fp);
+    return check_launch("frontend8_rgb_kernel");
+  }
   for (int pl = 0; pl < g.lay.n_planes; ++pl) {
     if (!((pl == 0 ? 1 : 2) & planes)) continue;
     long long per_img = (long long)g.lay.rows[pl] * g.lay.cols;
@@ -770,7 +784,8 @@ LRFB_EXPORT int32_t lrfb_qmf_encode(const lrfb_qmf_config* cfg, int32_t batch, c
                            reinterpret_cast<double*>(ws + m.gram[pl]), reinterpret_cast<double*>(ws + m.evec[pl]),
                            reinterpret_cast<double*>(ws + m.sigma[pl]), ws + m.total_bytes,
                            dbg && dbg->stop_after == 2, s, phase, cfg->input_dtype == LRFB_U8,
-                           pl == 0 && luma_gram_done);
+                           pl == 0 && luma_gram_done,
+                           cfg->input_dtype == LRFB_U8 && cfg->color_space == LRFB_RGB);
   };
   // The planes are independent.  When every plane runs the shared-memory-resident sweeps (no shared scratch),
   // the chroma work goes to a low-priority helper stream: the luma sweeps occupy 15 clusters x 8 SMs, the
@@ -1012,7 +1027,7 @@ LRFB_EXPORT int32_t lrfb_svd_encode(const lrfb_qmf_config* cfg, int32_t batch, c
   unsigned char* scratch = ws + m.total_bytes + align_up((int64_t)batch * 16, 256);
   rc = factorize_batch(xs[0], batch, M, N, R, -1.f, 1.f, 1, u, v, nullptr, nullptr, 0, nullptr, nullptr,
                        dbg ? dbg->d_sign_flip[0] : nullptr, reinterpret_cast<double*>(ws + m.gram[0]), evec, sigma,
-                       scratch, 0, st, 1);
+                       scratch, 0, st, 1, false, false, cfg->input_dtype == LRFB_U8);
   if (rc) return rc;
   for (int m0 = 0; m0 < batch; m0 += 65535) {
     const int cnt = std::min(65535, batch - m0);

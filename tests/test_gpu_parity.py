@@ -40,6 +40,7 @@ def test_frontend_other_patches_rgb_and_kodim(gpu):
     pc.check_frontend(gpu, port.s_nat(4, 96, 80), patch=(4, 4))
     pc.check_frontend(gpu, port.s_nat(4, 96, 80), patch=(16, 16))
     pc.check_frontend(gpu, port.s_nat(4, 50, 70), color_space="RGB")
+    pc.check_frontend(gpu, port.s_nat(4, 52, 72), color_space="RGB")  # W % 8 == 0: vectorised RGB kernel, rows padded
     pc.check_frontend(gpu, golden_image(["png", "kodim01.png"]))
 
 

@@ -24,6 +24,7 @@ def test_frontend_other_patches_and_rgb(sim):
     pc.check_frontend(sim, port.s_nat(4, 96, 80), patch=(4, 4))
     pc.check_frontend(sim, port.s_nat(4, 96, 80), patch=(16, 16))
     pc.check_frontend(sim, port.s_nat(4, 50, 70), color_space="RGB")
+    pc.check_frontend(sim, port.s_nat(4, 52, 72), color_space="RGB")  # W % 8 == 0: vectorised RGB kernel, rows padded
 
 
 @pytest.mark.parametrize("name", ["snat7_45x70_q7", "snat8_101x131_q7", "snat9_128x192_q7"])
