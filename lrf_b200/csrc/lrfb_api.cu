@@ -1323,15 +1323,38 @@ void combine_into(Bytes& out, const std::vector<const Bytes*>& parts) {
   for (size_t i = parts.size() - 1; i >= 1; --i) put_be32(out, acc[i - 1]);
   for (const Bytes* p : parts) out.insert(out.end(), p->begin(), p->end());
 }
+// One deflate state per worker thread, reset per column: what zlib.compress(data, 9) / compress2 produce (deflateInit,
+// one deflate(Z_FINISH), deflateEnd) without re-allocating and re-zeroing ~270 KB of state for every 64-byte V column.
+struct Deflater {
+  z_stream zs;
+  bool ok;
+  Deflater() : ok(false) {
+    memset(&zs, 0, sizeof(zs));
+    ok = deflateInit(&zs, 9) == Z_OK;
+  }
+  ~Deflater() {
+    if (ok) deflateEnd(&zs);
+  }
+  int run(Bytes& out, const unsigned char* src, size_t n) {
+    if (!ok) return Z_MEM_ERROR;
+    if (deflateReset(&zs) != Z_OK) return Z_STREAM_ERROR;
+    out.resize(compressBound((uLong)n));
+    zs.next_in = const_cast<Bytef*>(src), zs.avail_in = (uInt)n;
+    zs.next_out = out.data(), zs.avail_out = (uInt)out.size();
+    const int rc = deflate(&zs, Z_FINISH);
+    if (rc != Z_STREAM_END) return rc == Z_OK ? Z_BUF_ERROR : rc;
+    out.resize(zs.total_out);
+    return Z_OK;
+  }
+};
+
 // encode_matrix (lrf/compression/utils.py:354-390) of one fiber-major factor: R columns of `rows` int8 each
-int encode_fibers(Bytes& out, const int8_t* fibers, int R, int rows, const char* dtype_name, std::vector<Bytes>& cols) {
+int encode_fibers(Bytes& out, const int8_t* fibers, int R, int rows, const char* dtype_name, std::vector<Bytes>& cols,
+                  Deflater& z) {
   cols.resize(R);
   for (int r = 0; r < R; ++r) {
-    uLongf cap = compressBound((uLong)rows);
-    cols[r].resize(cap);
-    int zr = compress2(cols[r].data(), &cap, reinterpret_cast<const Bytef*>(fibers) + (size_t)r * rows, (uLong)rows, 9);
+    const int zr = z.run(cols[r], reinterpret_cast<const unsigned char*>(fibers) + (size_t)r * rows, (size_t)rows);
     if (zr != Z_OK) return zr;
-    cols[r].resize(cap);
   }
   char hdr[96];
   int n = snprintf(hdr, sizeof(hdr), "{\"num_fibers\": %d, \"mode\": \"col\", \"dtype\": \"%s\"}", R, dtype_name);
@@ -1367,6 +1390,7 @@ LRFB_EXPORT int32_t lrfb_qmf_pack_host(const lrfb_qmf_config* cfg, int32_t batch
   std::atomic<int> next{0}, err{0};
   auto work = [&]() {
     std::vector<Bytes> cols;
+    Deflater z;
     Bytes meta(metadata_json, metadata_json + metadata_len), body, img;
     std::vector<Bytes> enc(2 * L.n_planes);
     for (;;) {
@@ -1375,9 +1399,9 @@ LRFB_EXPORT int32_t lrfb_qmf_pack_host(const lrfb_qmf_config* cfg, int32_t batch
       const int8_t* rec = h_records + (size_t)i * L.record_bytes;
       for (int pl = 0; pl < L.n_planes; ++pl) {
         enc[2 * pl].clear(), enc[2 * pl + 1].clear();
-        int z = encode_fibers(enc[2 * pl], rec + L.u_offset[pl], L.rank[pl], L.rows[pl], "int8", cols);
-        if (!z) z = encode_fibers(enc[2 * pl + 1], rec + L.v_offset[pl], L.rank[pl], L.cols, "int8", cols);
-        if (z) err.store(z);
+        int zr = encode_fibers(enc[2 * pl], rec + L.u_offset[pl], L.rank[pl], L.rows[pl], "int8", cols, z);
+        if (!zr) zr = encode_fibers(enc[2 * pl + 1], rec + L.v_offset[pl], L.rank[pl], L.cols, "int8", cols, z);
+        if (zr) err.store(zr);
       }
       body.clear(), img.clear();
       std::vector<const Bytes*> ep;
