@@ -363,7 +363,7 @@ def main():
     achieved_tf = alg_flops / (bcd_ms / 1e3) / 1e12
     achieved_gbs = alg_bytes / (bcd_ms / 1e3) / 1e9
     # The kernel keeps X on chip for all ten sweeps, so it is bound by arithmetic, not by HBM: the roofline is FP32.
-    roofline = {"bound": "fp32", "kernel": "bcd_tc_kernel<4,768,384>: all 10 BCD sweeps on the luma planes (lrfb_bcd)",
+    roofline = {"bound": "fp32", "kernel": "bcd_tc_kernel<4,768,256>: all 10 BCD sweeps on the luma planes (lrfb_bcd)",
                 "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp32_peak,
                 "peak_source": "FP32 FFMA throughput measured in this run by lrfb_ffma_probe (MEASURED_PEAKS.json has no "
                                "FP32 entry; nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.5)",

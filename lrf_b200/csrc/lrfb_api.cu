@@ -374,14 +374,11 @@ template <int R>
 int launch_bcd_tc(const BcdBatch& b, cudaStream_t st) {
 #ifdef LRFB_DEV  // alternative shapes are instantiated in development builds only
   if (tc_variant() == 1 || (tc_variant() == 2 && R <= 2)) return launch_bcd_tc_cfg<R, 384, 192>(b, st);
-  if (tc_variant() == 3 || (tc_variant() == 4 && R == 4)) return launch_bcd_tc_cfg<R, 768, 256>(b, st);
 #endif
   if (b.M > 8 * kTcRows) return launch_bcd_tc_cfg<R, 768, 384, 16>(b, st);  // clusters of 16: up to 12 288 rows resident
-  // ranks 1 and 2 (chroma): 256 threads x 3 rows with two of them in registers — the FMA chains of a half-rank plane are
-  // bound by the shared-memory reads of X, which this shape cuts from 1/2 to 1/3 of the rows (19.37 -> 19.18 ms per step)
-  if constexpr (R <= 2) {
-    if (tc_variant() != 6) return launch_bcd_tc_cfg<R, 768, 256>(b, st);
-  }
+  // 256 threads x 3 rows with two of a thread's rows in registers: the FMA chains are bound by the shared-memory reads
+  // of X, which this shape cuts from 1/2 to 1/3 of the rows (luma 11.93 -> 11.68 ms, step 19.4 -> 19.05 ms)
+  if (tc_variant() != 6) return launch_bcd_tc_cfg<R, 768, 256>(b, st);
   return launch_bcd_tc_cfg<R, 768, 384>(b, st);
 }
 bool tc_enabled() {
