@@ -69,8 +69,9 @@ def test_gpu_svd_encode_parity(manifest, name):
     assert torch.equal(lrf_b200.svd_decode(blob), dec_ref_decoder)
     psnr = port.psnr(img, dec_ref_decoder)
     assert abs(psnr - e["psnr"]) <= 0.01, (psnr, e["psnr"])
-    # column signs are not aligned with LAPACK's here: the affine uint8 codes (hence zlib) move by a few %
-    assert abs(len(blob) - e["bytes"]) <= 0.08 * e["bytes"], (len(blob), e["bytes"])
+    # the dominant components carry LAPACK's signs (eig.cuh: closed-form rule for R <= 4, measured sign of the leading
+    # pair otherwise), so the affine uint8 codes see the reference's min / max: measured 0 - 0.08 % of the byte count
+    assert abs(len(blob) - e["bytes"]) <= 0.01 * e["bytes"], (len(blob), e["bytes"])
     # with LAPACK's signs the uint8 codes agree except at truncation boundaries
     meta, ur, vr = _ref_codes(golden_bytes(name))
     R = ur.shape[1]
