@@ -8,7 +8,7 @@ import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-OUT = os.path.join(CSRC, "build", "liblrfb.so")
+OUT = os.environ.get("LRFB_OUT") or os.path.join(CSRC, "build", "liblrfb.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -29,6 +29,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         cmd.insert(1, "-Xptxas=-v")
     if os.environ.get("LRFB_DEV"):  # development build: the library then honours its LRFB_* environment knobs
         cmd.insert(1, "-DLRFB_DEV")
+    for d in filter(None, os.environ.get("LRFB_DEFS", "").split(",")):  # experiment builds: extra -D switches
+        cmd.insert(1, "-D" + d)
     subprocess.check_call(cmd)
     return OUT
 

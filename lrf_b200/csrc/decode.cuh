@@ -225,6 +225,12 @@ qmf_decode8_kernel(const int8_t* __restrict__ factors, unsigned char* __restrict
 // word per pixel (PRMT), one DP4A per pixel instead of 4 x (convert, multiply, add).  The two rows share the luma U
 // word and the whole chroma reconstruction (nearest up-sampling).  Colour transform and u8 conversion as above.
 // ---------------------------------------------------------------------------------------------------
+// clamp to [0, 255] and truncate in one instruction (PTX: float-to-integer conversions saturate to the destination range)
+__device__ __forceinline__ unsigned f32_to_u8_sat(float x) {
+  unsigned r;
+  asm("cvt.rzi.u8.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ void transpose4x4_bytes(unsigned a, unsigned b, unsigned c, unsigned d, unsigned (&w)[4]) {
   const unsigned t0 = __byte_perm(a, b, 0x5140), t1 = __byte_perm(a, b, 0x7362);
   const unsigned u0 = __byte_perm(c, d, 0x5140), u1 = __byte_perm(c, d, 0x7362);
@@ -235,6 +241,9 @@ __device__ __forceinline__ void transpose4x4_bytes(unsigned a, unsigned b, unsig
 __global__ void __launch_bounds__(256)
 qmf_decode8x2_kernel(const int8_t* __restrict__ factors, unsigned char* __restrict__ out, DecodeParams P) {
   const float t[3][3] = {{1.0f, 0.0f, 1.40200f}, {1.0f, -0.344136f, -0.714136f}, {1.0f, 1.77200f, 0.0f}};
+  // V of the three planes, transposed once per image into DP4A operands: word [plane][position in the 8 x 8 patch]
+  // holds the (up to) four rank bytes of that position; every thread of the block reads the same words (broadcast)
+  __shared__ __align__(16) unsigned vt[3][64];
   const size_t hw = (size_t)P.H * P.W;
   const int segs = P.W / 8;
   const long long items = (long long)(P.H / 8) * segs;  // one item = one luma patch (8 rows x 8 pixels)
@@ -242,6 +251,14 @@ qmf_decode8x2_kernel(const int8_t* __restrict__ factors, unsigned char* __restri
   for (int im = blockIdx.y; im < P.n_img; im += gridDim.y) {
     const int8_t* rec = factors + (size_t)im * P.record_bytes;
     unsigned char* o = out + (size_t)im * 3 * hw;
+    __syncthreads();
+    if (threadIdx.x < 192) {
+      const int pl = threadIdx.x >> 6, pos = threadIdx.x & 63;
+      unsigned w = 0;
+      for (int r = 0; r < P.rank[pl]; ++r) w |= (unsigned)(unsigned char)rec[P.v_off[pl] + (size_t)r * 64 + pos] << (8 * r);
+      vt[pl][pos] = w;
+    }
+    __syncthreads();
     for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items;
          it += (long long)gridDim.x * blockDim.x) {
       const int pr = (int)(it / segs), sg = (int)(it - (long long)pr * segs);
@@ -249,7 +266,6 @@ qmf_decode8x2_kernel(const int8_t* __restrict__ factors, unsigned char* __restri
       // the byte gathers from the fiber-major factors and the index arithmetic are paid once per 64 pixels.
       const int m = pr * gy.nbw + sg;
       const int8_t* u = rec + P.u_off[0];
-      const int8_t* v = rec + P.v_off[0];
       unsigned uw = 0;
 #pragma unroll
       for (int r = 0; r < 4; ++r)
@@ -262,60 +278,41 @@ qmf_decode8x2_kernel(const int8_t* __restrict__ factors, unsigned char* __restri
         for (int r = 0; r < 4; ++r)
           if (r < P.rank[1 + pl])
             uwc[pl] |= (unsigned)(unsigned char)rec[P.u_off[1 + pl] + (size_t)r * gc.rows + mc] << (8 * r);
+      unsigned char* orow = o + (size_t)(8 * pr) * P.W + (size_t)sg * 8;
 #pragma unroll 1
       for (int q = 0; q < 4; ++q) {
         const int cy = 4 * pr + q;
         // ---- chroma: 4 columns 4*sg .. 4*sg+3 of chroma row cy, both planes ----
-        int pc[2][4];
-        {
-          const int col = (cy & 7) * 8 + (cx0 & 7);
-#pragma unroll
-          for (int pl = 0; pl < 2; ++pl) {
-            const int8_t* vc = rec + P.v_off[1 + pl];
-            unsigned vr[4] = {0, 0, 0, 0}, w[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-              if (r < P.rank[1 + pl]) vr[r] = *reinterpret_cast<const unsigned*>(vc + (size_t)r * 64 + col);
-            transpose4x4_bytes(vr[0], vr[1], vr[2], vr[3], w);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) pc[pl][j] = __dp4a((int)w[j], (int)uwc[pl], 0);
-          }
-        }
+        const int cpos = (cy & 7) * 8 + (cx0 & 7);
+        const uint4 wb = *reinterpret_cast<const uint4*>(&vt[1][cpos]), wr = *reinterpret_cast<const uint4*>(&vt[2][cpos]);
+        const unsigned wcb[4] = {wb.x, wb.y, wb.z, wb.w}, wcr[4] = {wr.x, wr.y, wr.z, wr.w};
         float cb[4], cr[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) cb[j] = __fadd_rn((float)pc[0][j], -128.0f), cr[j] = __fadd_rn((float)pc[1][j], -128.0f);
-        // ---- luma rows 2cy and 2cy+1 ----
+        for (int j = 0; j < 4; ++j) {
+          cb[j] = __fadd_rn((float)__dp4a((int)wcb[j], (int)uwc[0], 0), -128.0f);
+          cr[j] = __fadd_rn((float)__dp4a((int)wcr[j], (int)uwc[1], 0), -128.0f);
+        }
+        // ---- luma rows 2q and 2q+1 of the patch ----
 #pragma unroll
         for (int dy = 0; dy < 2; ++dy) {
-          const int y = 2 * cy + dy, col = (y & 7) * 8;
-          uint2 vr[4];
-#pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            vr[r] = make_uint2(0u, 0u);
-            if (r < P.rank[0]) vr[r] = *reinterpret_cast<const uint2*>(v + (size_t)r * 64 + col);
-          }
-          unsigned wl[4], wh[4];
-          transpose4x4_bytes(vr[0].x, vr[1].x, vr[2].x, vr[3].x, wl);
-          transpose4x4_bytes(vr[0].y, vr[1].y, vr[2].y, vr[3].y, wh);
+          const int row = 2 * q + dy;
+          const uint4 w0 = *reinterpret_cast<const uint4*>(&vt[0][row * 8]), w1 = *reinterpret_cast<const uint4*>(&vt[0][row * 8 + 4]);
+          const unsigned wy[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
           unsigned px[3][8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float yv = (float)__dp4a((int)(j < 4 ? wl[j & 3] : wh[j & 3]), (int)uw, 0);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              float acc = __fmul_rn(t[c][0], yv);
-              acc = __fmaf_rn(t[c][1], cb[j >> 1], acc);
-              acc = __fmaf_rn(t[c][2], cr[j >> 1], acc);
-              acc = fminf(fmaxf(acc, 0.0f), 255.0f);
-              px[c][j] = __float_as_uint(__fadd_rz(acc, 8388608.0f));  // pixel value in the low byte
-            }
+            const float yv = (float)__dp4a((int)wy[j], (int)uw, 0);
+            // t[c][0] = 1 and the zero coefficients drop out exactly (1*y = y; fma(0, c, a) = a up to the sign of a
+            // zero, which the conversion maps to 0 either way); the saturating conversion is clamp + truncate
+            px[0][j] = f32_to_u8_sat(__fmaf_rn(t[0][2], cr[j >> 1], yv));
+            px[1][j] = f32_to_u8_sat(__fmaf_rn(t[1][2], cr[j >> 1], __fmaf_rn(t[1][1], cb[j >> 1], yv)));
+            px[2][j] = f32_to_u8_sat(__fmaf_rn(t[2][1], cb[j >> 1], yv));
           }
-          const size_t off = (size_t)y * P.W + (size_t)sg * 8;
 #pragma unroll
           for (int c = 0; c < 3; ++c) {  // low bytes of 4 words -> one word: 3 PRMT
             const unsigned lo = __byte_perm(__byte_perm(px[c][0], px[c][1], 0x0040), __byte_perm(px[c][2], px[c][3], 0x0040), 0x5410);
             const unsigned hi = __byte_perm(__byte_perm(px[c][4], px[c][5], 0x0040), __byte_perm(px[c][6], px[c][7], 0x0040), 0x5410);
-            *reinterpret_cast<uint2*>(o + c * hw + off) = make_uint2(lo, hi);
+            *reinterpret_cast<uint2*>(orow + c * hw + (size_t)row * P.W) = make_uint2(lo, hi);
           }
         }
       }

@@ -1034,15 +1034,21 @@ LRFB_EXPORT int32_t lrfb_svd_encode(const lrfb_qmf_config* cfg, int32_t batch, c
   for (int m0 = 0; m0 < batch; m0 += 65535) {
     const int cnt = std::min(65535, batch - m0);
     const int gx = std::max(1, std::min((M + kProjRows - 1) / kProjRows, 256));
-    const size_t psmem = (size_t)N * R * 8 + (size_t)kProjRows * (N + 1) * 4;
+    const size_t psmem = (size_t)N * kProjCols * 8;
+    const bool vec = N % 4 == 0;
 #ifndef LRFB_SIM
     if (psmem > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(svd_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
+      cudaError_t e = vec ? cudaFuncSetAttribute(svd_project_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem)
+                          : cudaFuncSetAttribute(svd_project_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
       if (e != cudaSuccess) return fail((int)e, "project smem attribute: %s", cudaGetErrorString(e));
     }
 #endif
-    LRFB_LAUNCH(svd_project_kernel, dim3(gx, cnt), dim3(kProjRows), psmem, st, xs[0] + (size_t)m0 * M * N,
-                (long long)M * N, M, N, R, evec + (size_t)m0 * N * R, sigma + (size_t)m0 * R, u + (size_t)m0 * M * R);
+    if (vec)
+      LRFB_LAUNCH(svd_project_kernel<true>, dim3(gx, cnt), dim3(kProjRows), psmem, st, xs[0] + (size_t)m0 * M * N,
+                  (long long)M * N, M, N, R, evec + (size_t)m0 * N * R, sigma + (size_t)m0 * R, u + (size_t)m0 * M * R);
+    else
+      LRFB_LAUNCH(svd_project_kernel<false>, dim3(gx, cnt), dim3(kProjRows), psmem, st, xs[0] + (size_t)m0 * M * N,
+                  (long long)M * N, M, N, R, evec + (size_t)m0 * N * R, sigma + (size_t)m0 * R, u + (size_t)m0 * M * R);
     if ((rc = check_launch("svd_project_kernel"))) return rc;
   }
   LRFB_LAUNCH(minmax_kernel, dim3(batch), dim3(256), 0, st, u, (long long)M * R, mm);

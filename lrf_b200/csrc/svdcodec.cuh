@@ -11,62 +11,85 @@
 
 namespace lrfb {
 
-constexpr int kProjRows = 128;  // rows per CTA tile (= threads per CTA)
+constexpr int kProjRows = 128;  // rows per CTA tile
+constexpr int kProjCols = 16;   // columns of U per pass
 
-// grid = (row tiles, matrices).  X tile staged through shared memory with coalesced loads (row stride
-// N+1: conflict-free for the thread-per-row reads).  u[m][r] = f32(X[m]·E[:,r] / sigma_r) * sqrtf(f32(sigma_r)),
-// the dot product in f64 (u_hat is then the correctly rounded f32 of the true left singular vector entry).
+// grid = (row tiles, matrices), 128 threads.  u[m][r] = f32(X[m]·E[:,r] / sigma_r) * sqrtf(f32(sigma_r)), the dot
+// product in f64 with k ascending (u_hat is then the correctly rounded f32 of the true left singular vector entry).
+// Register tile: warp w owns columns 4w..4w+3 of a 16-column pass, lane l the rows l, l+32, l+64, l+96 of the tile —
+// 16 independent DFMA chains per thread fed by 4 row loads (16 bytes each when N % 4 == 0; the other 16 bytes of the
+// sector are the next step's, an L1 hit) and 2 broadcast 16-byte reads of E per k, so the FP64 pipe is the limit.
+template <bool VEC>
 __global__ void __launch_bounds__(kProjRows)
 svd_project_kernel(const float* __restrict__ X, long long x_stride, int M, int N, int R,
                    const double* __restrict__ evec, const double* __restrict__ sigma, float* __restrict__ U) {
   LRFB_DYN_SMEM(smem_raw);
-  double* ev = reinterpret_cast<double*>(smem_raw);          // [N][R]
-  float* xt = reinterpret_cast<float*>(ev + (size_t)N * R);  // [kProjRows][N+1]
+  double* ev = reinterpret_cast<double*>(smem_raw);  // [N][16]: the current pass's columns, zero padded
   const int mat = blockIdx.y;
   const int keep = min(R, min(M, N));
-  const int XS = N + 1;
-  for (int i = threadIdx.x; i < N * R; i += blockDim.x) ev[i] = evec[(size_t)mat * N * R + i];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* x = X + (size_t)mat * x_stride;
   float* u = U + (size_t)mat * M * R;
   const double* sg = sigma + (size_t)mat * R;
-  for (int r0 = blockIdx.x * kProjRows; r0 < M; r0 += gridDim.x * kProjRows) {
-    const int valid = min(kProjRows, M - r0);
+  const double* E = evec + (size_t)mat * N * R;
+  for (int c0 = 0; c0 < R; c0 += kProjCols) {
     __syncthreads();
-    for (int i = threadIdx.x; i < valid * N; i += blockDim.x) {  // coalesced: consecutive threads, consecutive elements
-      const int row = i / N, c = i - row * N;
-      xt[row * XS + c] = x[(size_t)r0 * N + i];
+    for (int i = threadIdx.x; i < N * kProjCols; i += blockDim.x) {
+      const int k = i / kProjCols, j = i % kProjCols;
+      ev[i] = c0 + j < R ? E[(size_t)k * R + c0 + j] : 0.0;
     }
     __syncthreads();
-    const int m = threadIdx.x;
-    if (m < valid) {
-      for (int c0 = 0; c0 < R; c0 += 16) {  // up to 16 columns per pass over the row
-        double acc[16];
+    for (int r0 = blockIdx.x * kProjRows; r0 < M; r0 += gridDim.x * kProjRows) {
+      const float* xr[4];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = 0.0;
-        const int nc = min(16, R - c0);
-        if (nc == 16) {
-#pragma unroll 2
-          for (int k = 0; k < N; ++k) {
-            const double xv = (double)xt[m * XS + k];
+      for (int i = 0; i < 4; ++i) xr[i] = x + (size_t)min(r0 + lane + 32 * i, M - 1) * N;  // rows past M: clamped, not stored
+      double acc[4][4];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) acc[j] = fma(xv, ev[k * R + c0 + j], acc[j]);
-          }
-        } else {
-#pragma unroll 2
-          for (int k = 0; k < N; ++k) {
-            const double xv = (double)xt[m * XS + k];
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (j < nc) acc[j] = fma(xv, ev[k * R + c0 + j], acc[j]);
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+      const double* ew = ev + 4 * warp;
+      if (VEC) {
+        for (int k = 0; k < N; k += 4) {
+          float4 xv[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) xv[i] = *reinterpret_cast<const float4*>(xr[i] + k);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            double e[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) e[j] = ew[(k + kk) * kProjCols + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const double xd = (double)(kk == 0 ? xv[i].x : kk == 1 ? xv[i].y : kk == 2 ? xv[i].z : xv[i].w);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) acc[i][j] = fma(xd, e[j], acc[i][j]);
+            }
           }
         }
+      } else {
+        for (int k = 0; k < N; ++k) {
+          double e[4];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int r = c0 + j;
-          if (j < nc) {
+          for (int j = 0; j < 4; ++j) e[j] = ew[k * kProjCols + j];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const double xd = (double)xr[i][k];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fma(xd, e[j], acc[i][j]);
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int m = r0 + lane + 32 * i;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int r = c0 + 4 * warp + j;
+          if (m < M && r < R) {
             float val = 0.0f;
-            if (r < keep && sg[r] > 0.0) val = __fmul_rn((float)(acc[j] / sg[r]), __fsqrt_rn((float)sg[r]));
-            u[(size_t)(r0 + m) * R + r] = val;
+            if (r < keep && sg[r] > 0.0) val = __fmul_rn((float)(acc[i][j] / sg[r]), __fsqrt_rn((float)sg[r]));
+            u[(size_t)m * R + r] = val;
           }
         }
       }
