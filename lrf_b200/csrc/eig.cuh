@@ -264,6 +264,130 @@ __device__ __forceinline__ bool sign_rule_applies(int M_rows, int N, int R) {
   return R <= 4 && N >= 8 && 2 * M_rows >= 3 * N;
 }
 
+// Warp-collective: the R largest eigenpairs of the leading L x L block of tridiag(d, e).  lam[R] descending, z[r][0..N)
+// unit vectors (zero beyond L), lu: R x 5N doubles of scratch.  wide_mgs: the Gram–Schmidt clean-up runs on all lanes
+// (different summation order in the last bits) instead of serially on lane 0.
+__device__ inline void tridiag_topr_warp(const double* d, const double* e, int L, int N, int R, double* lam, double* z,
+                                         double* lu, int lane, bool wide_mgs) {
+  // ---- 2. R largest eigenvalues by multisection ------------------------------------------------
+  double glo = d[0], ghi = d[0], maxe2 = 0.0;
+#pragma unroll 1
+  for (int i = 0; i < L; ++i) {  // Gershgorin bounds, redundantly per lane
+    double r = (i > 0 ? fabs(e[i - 1]) : 0.0) + (i < L - 1 ? fabs(e[i]) : 0.0);
+    glo = fmin(glo, d[i] - r);
+    ghi = fmax(ghi, d[i] + r);
+    if (i < L - 1) maxe2 = fmax(maxe2, e[i] * e[i]);
+  }
+  const double tnorm = fmax(fabs(glo), fabs(ghi));
+  const double pivmin = 1e-290 * fmax(1.0, maxe2);
+  glo -= 2.3e-16 * tnorm * L + pivmin;
+  ghi += 2.3e-16 * tnorm * L + pivmin;
+  int ppe = 32;  // probes per eigenvalue: largest power of two with (32 / ppe) >= min(R, 32)
+  while (ppe > 1 && 32 / ppe < min(R, 32)) ppe >>= 1;
+  const int groups = 32 / ppe;
+  int rounds = 1;  // (ppe+1)^rounds >= 2^46: eigenvalues to ~1e-14 of ||T|| (sigma is rounded to f32,
+  {                 // and inverse iteration only needs the shift to be much closer than the gaps)
+    double shrink = 1.0;
+    while (shrink < 7.0e13) shrink *= (double)(ppe + 1), ++rounds;
+  }
+  for (int r0 = 0; r0 < R; r0 += groups) {
+    const int grp = lane / ppe, pr = lane % ppe;
+    const int r = r0 + grp;
+    const bool active = r < R;
+    const int idx = L - 1 - r;  // ascending index of the r-th largest
+    double lo = glo, hi = ghi;
+#pragma unroll 1
+    for (int round = 0; round < rounds; ++round) {
+      const double step = (hi - lo) / (double)(ppe + 1);
+      const double x = lo + step * (double)(pr + 1);
+      const int cnt = active ? sturm_count(d, e, L, x, pivmin) : 0;
+      const unsigned ballot = __ballot_sync(0xffffffffu, active && cnt > idx);
+      const unsigned bits = (ppe == 32) ? ballot : ((ballot >> (grp * ppe)) & ((1u << ppe) - 1u));
+      const int f = bits ? (__ffs((int)bits) - 1) : ppe;  // first probe with count > idx
+      const double nlo = (f == 0) ? lo : lo + step * (double)f;
+      const double nhi = (f == ppe) ? hi : lo + step * (double)(f + 1);
+      lo = nlo, hi = nhi;
+    }
+    if (active && pr == 0) lam[r] = 0.5 * (lo + hi);
+  }
+  __syncwarp();
+
+  // ---- 3. eigenvectors of the tridiagonal (leading L x L block) ---------------------------------------
+  for (int r = lane; r < R; r += 32)
+  {
+    tridiag_inverse_iteration(d, e, L, lam[r], tnorm, z + r * N, lu + r * 5 * N, r);
+    for (int i = L; i < N; ++i) z[r * N + i] = 0.0;
+  }
+  __syncwarp();
+  if (wide_mgs) {  // modified Gram–Schmidt in eigenvalue order, lanes strided over the L live entries
+    for (int r = 0; r < R; ++r) {
+      double* zr = z + r * N;
+      for (int q = 0; q < r; ++q) {
+        const double* zq = z + q * N;
+        double dot = 0.0;
+        for (int i = lane; i < L; i += 32) dot = fma(zr[i], zq[i], dot);
+        dot = warp_sum(dot);
+        for (int i = lane; i < L; i += 32) zr[i] = fma(-dot, zq[i], zr[i]);
+        __syncwarp();
+      }
+      double nrm = 0.0;
+      for (int i = lane; i < L; i += 32) nrm = fma(zr[i], zr[i], nrm);
+      nrm = warp_sum(nrm);
+      if (nrm < 1e-20) {  // degenerate (rank-deficient input, SURVEY H10): fall back to a basis vector
+        for (int i = lane; i < N; i += 32) zr[i] = (i == (r % N)) ? 1.0 : 0.0;
+        __syncwarp();
+        for (int q = 0; q < r; ++q) {
+          const double* zq = z + q * N;
+          const double dot = zq[r % N];
+          for (int i = lane; i < N; i += 32) zr[i] = fma(-dot, zq[i], zr[i]);
+          __syncwarp();
+        }
+        nrm = 0.0;
+        for (int i = lane; i < N; i += 32) nrm = fma(zr[i], zr[i], nrm);
+        nrm = warp_sum(nrm);
+        if (nrm < 1e-20) nrm = 1.0;
+      }
+      nrm = 1.0 / sqrt(nrm);
+      for (int i = lane; i < N; i += 32) zr[i] *= nrm;
+      __syncwarp();
+    }
+  } else
+  if (lane == 0) {  // modified Gram–Schmidt in eigenvalue order (only matters for near-multiple eigenvalues)
+    for (int r = 0; r < R; ++r) {
+      double* zr = z + r * N;
+      for (int q = 0; q < r; ++q) {
+        const double* zq = z + q * N;
+        double dot = 0.0;
+#pragma unroll 1
+        for (int i = 0; i < N; ++i) dot = fma(zr[i], zq[i], dot);
+#pragma unroll 1
+        for (int i = 0; i < N; ++i) zr[i] = fma(-dot, zq[i], zr[i]);
+      }
+      double nrm = 0.0;
+#pragma unroll 1
+      for (int i = 0; i < N; ++i) nrm = fma(zr[i], zr[i], nrm);
+      if (nrm < 1e-20) {  // degenerate (rank-deficient input, SURVEY H10): fall back to a basis vector
+#pragma unroll 1
+        for (int i = 0; i < N; ++i) zr[i] = (i == (r % N)) ? 1.0 : 0.0;
+        for (int q = 0; q < r; ++q) {
+          const double* zq = z + q * N;
+          double dot = zq[r % N];
+#pragma unroll 1
+          for (int i = 0; i < N; ++i) zr[i] = fma(-dot, zq[i], zr[i]);
+        }
+        nrm = 0.0;
+#pragma unroll 1
+        for (int i = 0; i < N; ++i) nrm = fma(zr[i], zr[i], nrm);
+        if (nrm < 1e-20) nrm = 1.0;
+      }
+      nrm = 1.0 / sqrt(nrm);
+#pragma unroll 1
+      for (int i = 0; i < N; ++i) zr[i] *= nrm;
+    }
+  }
+  __syncwarp();
+}
+
 // One warp (= one CTA of 32 threads) per matrix.  Gin: [n][N][N] symmetric (overwritten when the
 // working copy stays in global memory).  Outputs per matrix: evec[N][R] (unit, sign-fixed, row-major)
 // and sigma[R] = sqrt(max(lambda, 0)).  sign_flip: optional [n][R] of +1/-1 multiplied onto the
@@ -367,94 +491,7 @@ eig_topr_kernel(const double* __restrict__ Gin, int Nrt, int R, double* __restri
     __syncwarp();
   }
   };
-  double tnorm_out = 0.0;
-  auto solve = [&](int L) {
-  // ---- 2. R largest eigenvalues by multisection ------------------------------------------------
-  double glo = d[0], ghi = d[0], maxe2 = 0.0;
-#pragma unroll 1
-  for (int i = 0; i < L; ++i) {  // Gershgorin bounds, redundantly per lane
-    double r = (i > 0 ? fabs(e[i - 1]) : 0.0) + (i < L - 1 ? fabs(e[i]) : 0.0);
-    glo = fmin(glo, d[i] - r);
-    ghi = fmax(ghi, d[i] + r);
-    if (i < L - 1) maxe2 = fmax(maxe2, e[i] * e[i]);
-  }
-  const double tnorm = fmax(fabs(glo), fabs(ghi));
-  const double pivmin = 1e-290 * fmax(1.0, maxe2);
-  glo -= 2.3e-16 * tnorm * L + pivmin;
-  ghi += 2.3e-16 * tnorm * L + pivmin;
-  int ppe = 32;  // probes per eigenvalue: largest power of two with (32 / ppe) >= min(R, 32)
-  while (ppe > 1 && 32 / ppe < min(R, 32)) ppe >>= 1;
-  const int groups = 32 / ppe;
-  int rounds = 1;  // (ppe+1)^rounds >= 2^46: eigenvalues to ~1e-14 of ||T|| (sigma is rounded to f32,
-  {                 // and inverse iteration only needs the shift to be much closer than the gaps)
-    double shrink = 1.0;
-    while (shrink < 7.0e13) shrink *= (double)(ppe + 1), ++rounds;
-  }
-  for (int r0 = 0; r0 < R; r0 += groups) {
-    const int grp = lane / ppe, pr = lane % ppe;
-    const int r = r0 + grp;
-    const bool active = r < R;
-    const int idx = L - 1 - r;  // ascending index of the r-th largest
-    double lo = glo, hi = ghi;
-#pragma unroll 1
-    for (int round = 0; round < rounds; ++round) {
-      const double step = (hi - lo) / (double)(ppe + 1);
-      const double x = lo + step * (double)(pr + 1);
-      const int cnt = active ? sturm_count(d, e, L, x, pivmin) : 0;
-      const unsigned ballot = __ballot_sync(0xffffffffu, active && cnt > idx);
-      const unsigned bits = (ppe == 32) ? ballot : ((ballot >> (grp * ppe)) & ((1u << ppe) - 1u));
-      const int f = bits ? (__ffs((int)bits) - 1) : ppe;  // first probe with count > idx
-      const double nlo = (f == 0) ? lo : lo + step * (double)f;
-      const double nhi = (f == ppe) ? hi : lo + step * (double)(f + 1);
-      lo = nlo, hi = nhi;
-    }
-    if (active && pr == 0) lam[r] = 0.5 * (lo + hi);
-  }
-  __syncwarp();
-
-  // ---- 3. eigenvectors of the tridiagonal (leading L x L block) ---------------------------------------
-  for (int r = lane; r < R; r += 32)
-  {
-    tridiag_inverse_iteration(d, e, L, lam[r], tnorm, z + r * N, lu + r * 5 * N, r);
-    for (int i = L; i < N; ++i) z[r * N + i] = 0.0;
-  }
-  __syncwarp();
-  if (lane == 0) {  // modified Gram–Schmidt in eigenvalue order (only matters for near-multiple eigenvalues)
-    for (int r = 0; r < R; ++r) {
-      double* zr = z + r * N;
-      for (int q = 0; q < r; ++q) {
-        const double* zq = z + q * N;
-        double dot = 0.0;
-#pragma unroll 1
-        for (int i = 0; i < N; ++i) dot = fma(zr[i], zq[i], dot);
-#pragma unroll 1
-        for (int i = 0; i < N; ++i) zr[i] = fma(-dot, zq[i], zr[i]);
-      }
-      double nrm = 0.0;
-#pragma unroll 1
-      for (int i = 0; i < N; ++i) nrm = fma(zr[i], zr[i], nrm);
-      if (nrm < 1e-20) {  // degenerate (rank-deficient input, SURVEY H10): fall back to a basis vector
-#pragma unroll 1
-        for (int i = 0; i < N; ++i) zr[i] = (i == (r % N)) ? 1.0 : 0.0;
-        for (int q = 0; q < r; ++q) {
-          const double* zq = z + q * N;
-          double dot = zq[r % N];
-#pragma unroll 1
-          for (int i = 0; i < N; ++i) zr[i] = fma(-dot, zq[i], zr[i]);
-        }
-        nrm = 0.0;
-#pragma unroll 1
-        for (int i = 0; i < N; ++i) nrm = fma(zr[i], zr[i], nrm);
-        if (nrm < 1e-20) nrm = 1.0;
-      }
-      nrm = 1.0 / sqrt(nrm);
-#pragma unroll 1
-      for (int i = 0; i < N; ++i) zr[i] *= nrm;
-    }
-  }
-  __syncwarp();
-
-  };
+  auto solve = [&](int L) { tridiag_topr_warp(d, e, L, N, R, lam, z, lu, lane, false); };
   int n_refl = N - 2;  // reflectors formed
   {
     const int k_fast = min(N - 2, max(23, 4 * R + 23));
