@@ -187,6 +187,20 @@ int32_t lrfb_qmf_pack_host(const lrfb_qmf_config* cfg, int32_t batch, const int8
                            const char* metadata_json, int64_t metadata_len, uint8_t* h_out, int64_t out_stride,
                            int64_t* out_sizes, int32_t threads);
 
+/* Lossless stage on the device — the same tail of lrf.qmf_encode (lrf/compression/qmf.py:288-292; encode_matrix:
+ * zlib.compress(column, level=9), lrf/compression/utils.py:354-390; combine_bytes :246-300), produced on the GPU byte
+ * for byte: one warp deflates one factor column with zlib's level-9 algorithm restated (lrf_b200/csrc/deflate9.cuh),
+ * then every image is framed.  d_records: [batch][record_bytes] as lrfb_qmf_encode writes them (device memory);
+ * image i's stream is d_blob[d_offsets[i] .. d_offsets[i+1]) (d_offsets: batch + 1 int64 in device memory, streams packed
+ * back to back).  blob_capacity >= batch * lrfb_qmf_pack_bound(cfg, metadata_len) always suffices; when
+ * d_offsets[batch] > blob_capacity the images that did not fit are not written (check after the copy back).
+ * Columns longer than 16 382 bytes (one deflate block, no window slide) return LRFB_E_UNSUPPORTED and
+ * lrfb_qmf_pack_device_workspace returns -1: use lrfb_qmf_pack_host for those shapes. */
+int64_t lrfb_qmf_pack_device_workspace(const lrfb_qmf_config* cfg, int32_t batch);
+int32_t lrfb_qmf_pack_device(const lrfb_qmf_config* cfg, int32_t batch, const int8_t* d_records,
+                             const char* metadata_json, int64_t metadata_len, uint8_t* d_blob, int64_t blob_capacity,
+                             int64_t* d_offsets, void* d_workspace, int64_t workspace_bytes, void* stream);
+
 /* Test hook: select a kernel variant process-wide.  Knobs: "decode_v1" (1 = per-row float decoder instead of the
  * int8 dot-product one).  The shipped library reads no environment variables. */
 int32_t lrfb_debug_set(const char* knob, int32_t value);

@@ -54,6 +54,39 @@ def pack_records(records: np.ndarray, cfg, lay, meta: dict, threads: int = 0) ->
     return [out[i, : sizes[i]].tobytes() for i in range(B)]
 
 
+def device_packer_supported(cfg, batch: int = 1) -> bool:
+    """True when every factor column of this shape fits the device deflate (at most 16 382 bytes per column)."""
+    return int(_cabi.lib().lrfb_qmf_pack_device_workspace(C.byref(cfg), batch)) > 0
+
+
+def pack_records_device(records: torch.Tensor, cfg, lay, meta: dict) -> list[bytes]:
+    """int8 factor records (B, record_bytes) ON THE DEVICE + metadata → B encoded ``bytes``: the zlib level-9 streams
+    and the reference's framing are produced by ``lrfb_qmf_pack_device`` (one warp per factor column, byte-identical to
+    zlib: lrf_b200/csrc/deflate9.cuh); only the finished streams (about a fifth of the raw factors) cross PCIe."""
+    assert records.is_cuda and records.dtype == torch.int8 and records.ndim == 2 and records.shape[1] == lay.record_bytes
+    records = records.contiguous()
+    B = records.shape[0]
+    mj = packing.dict_to_bytes(meta)
+    lib = _cabi.lib()
+    wsb = int(lib.lrfb_qmf_pack_device_workspace(C.byref(cfg), B))
+    if wsb <= 0:
+        raise _cabi.LrfbError("lrfb_qmf_pack_device: " + (lib.lrfb_last_error() or b"unsupported shape").decode())
+    cap = B * int(lib.lrfb_qmf_pack_bound(C.byref(cfg), len(mj)))
+    with torch.cuda.device(records.device):
+        ws = torch.empty(wsb, dtype=torch.uint8, device=records.device)
+        blob = torch.empty(cap, dtype=torch.uint8, device=records.device)
+        offs = torch.empty(B + 1, dtype=torch.int64, device=records.device)
+        rc = lib.lrfb_qmf_pack_device(C.byref(cfg), B, C.c_void_p(records.data_ptr()), mj, len(mj),
+                                      C.c_void_p(blob.data_ptr()), cap, C.c_void_p(offs.data_ptr()),
+                                      C.c_void_p(ws.data_ptr()), wsb, _stream_ptr())
+        _cabi.check(rc, "lrfb_qmf_pack_device")
+        o = offs.cpu().numpy()
+        assert o[B] <= cap
+        host = blob[: int(o[B])].cpu().numpy()
+    mv = memoryview(host)
+    return [bytes(mv[o[i] : o[i + 1]]) for i in range(B)]
+
+
 def _require_cuda() -> None:
     if not torch.cuda.is_available():
         raise _cabi.LrfbError("lrf_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
@@ -203,8 +236,10 @@ def qmf_encode_batch(images: torch.Tensor, rank=None, quality=None, color_space:
         meta = _metadata(images.dtype, color_space, patch, bounds, patch_size, lay)
         if return_records:
             return records, lay, meta
+        if device_packer_supported(cfg, B):
+            return pack_records_device(records, cfg, lay, meta)
         host = records.cpu().numpy()
-    return pack_records(host, cfg, lay, meta)
+    return pack_records(host, cfg, lay, meta)  # columns above 16 382 bytes: zlib on the host thread pool
 
 
 def qmf_encode(image: torch.Tensor, rank=None, quality=None, color_space: str = "YCbCr",

@@ -20,6 +20,7 @@
 #include "bcd_resident.cuh"
 #include "bcd_tc.cuh"
 #include "decode.cuh"
+#include "deflate9.cuh"
 #include "eig.cuh"
 #include "frontend.cuh"
 #include "frontgram.cuh"
@@ -1431,6 +1432,145 @@ LRFB_EXPORT int32_t lrfb_qmf_pack_host(const lrfb_qmf_config* cfg, int32_t batch
   if (err.load()) return fail(LRFB_E_UNSUPPORTED, "zlib / packing failed (%d)", err.load());
   return 0;
 }
+
+// ---- lossless stage on the device: every factor column deflated by one warp (deflate9.cuh), then framed ----------------
+
+namespace {
+struct PackPlan {
+  lrfb_qmf_layout L;
+  int n_mat, cols_total;
+  int len[6], ncols[6], col0[6], slot[6], slot_off[6];
+  long long rec_off[6];
+  long long img_stride;     // column-buffer bytes per image
+  int n_groups;
+  int group_len[6];         // distinct column lengths, longest first
+  int grid[6];
+  long long off_cbuf, off_csize, off_sizes, off_counter, off_scratch, total;
+};
+int ctas_per_sm(int len) {
+  const int per = d9::smem_bytes(len) + 1024;  // 1 KB of system-reserved shared memory per CTA
+  return std::max(1, std::min(32, (227 * 1024) / per));
+}
+int make_pack_plan(const lrfb_qmf_config* cfg, int batch, PackPlan& P) {
+  int rc = lrfb_qmf_layout_query(cfg, &P.L);
+  if (rc) return rc;
+  const lrfb_qmf_layout& L = P.L;
+  P.n_mat = 2 * L.n_planes, P.cols_total = 0;
+  long long so = 0;
+  P.n_groups = 0;
+  for (int mtx = 0; mtx < P.n_mat; ++mtx) {
+    const int pl = mtx >> 1;
+    P.len[mtx] = (mtx & 1) ? L.cols : L.rows[pl];
+    P.rec_off[mtx] = (mtx & 1) ? L.v_offset[pl] : L.u_offset[pl];
+    P.ncols[mtx] = L.rank[pl];
+    if (P.len[mtx] > d9::kMaxLen) return fail(LRFB_E_UNSUPPORTED, "column of %d bytes: the device deflate takes at most %d (use lrfb_qmf_pack_host)", P.len[mtx], d9::kMaxLen);
+    if (P.ncols[mtx] > 64) return fail(LRFB_E_UNSUPPORTED, "rank above 64");
+    P.col0[mtx] = P.cols_total, P.cols_total += P.ncols[mtx];
+    P.slot[mtx] = (P.len[mtx] + 16 + 15) & ~15;
+    P.slot_off[mtx] = (int)so, so += (long long)P.ncols[mtx] * P.slot[mtx];
+    bool seen = false;
+    for (int g = 0; g < P.n_groups; ++g) seen |= P.group_len[g] == P.len[mtx];
+    if (!seen) P.group_len[P.n_groups++] = P.len[mtx];
+  }
+  if (so > 0x7fffffffll) return fail(LRFB_E_UNSUPPORTED, "image record too large");
+  std::sort(P.group_len, P.group_len + P.n_groups, [](int a, int b) { return a > b; });
+  P.img_stride = so;
+  long long scratch = 0;
+  for (int g = 0; g < P.n_groups; ++g) {
+    long long streams = 0;
+    for (int mtx = 0; mtx < P.n_mat; ++mtx)
+      if (P.len[mtx] == P.group_len[g]) streams += (long long)batch * P.ncols[mtx];
+    P.grid[g] = (int)std::min<long long>(streams, (long long)num_sms() * ctas_per_sm(P.group_len[g]));
+    scratch = std::max(scratch, P.grid[g] * d9::scratch_per_cta(P.group_len[g]));
+  }
+  auto up = [](long long v) { return (v + 255) & ~255ll; };
+  long long o = 0;
+  P.off_cbuf = o, o = up(o + (long long)batch * P.img_stride);
+  P.off_csize = o, o = up(o + 4ll * batch * P.cols_total);
+  P.off_sizes = o, o = up(o + 8ll * batch);
+  P.off_counter = o, o = up(o + 64);
+  P.off_scratch = o, o = up(o + scratch);
+  P.total = o;
+  return 0;
+}
+}  // namespace
+
+LRFB_EXPORT int64_t lrfb_qmf_pack_device_workspace(const lrfb_qmf_config* cfg, int32_t batch) {
+  PackPlan P;
+  if (batch <= 0 || make_pack_plan(cfg, batch, P)) return -1;
+  return P.total;
+}
+
+LRFB_EXPORT int32_t lrfb_qmf_pack_device(const lrfb_qmf_config* cfg, int32_t batch, const int8_t* d_records,
+                                         const char* metadata_json, int64_t metadata_len, uint8_t* d_blob,
+                                         int64_t blob_capacity, int64_t* d_offsets, void* d_workspace,
+                                         int64_t workspace_bytes, void* stream) {
+  if (!d_records || !metadata_json || !d_blob || !d_offsets || !d_workspace || batch <= 0 || metadata_len <= 0)
+    return fail(LRFB_E_ARG, "bad arguments");
+  if (metadata_len > 1024) return fail(LRFB_E_UNSUPPORTED, "metadata json above 1024 bytes");
+  PackPlan P;
+  int rc = make_pack_plan(cfg, batch, P);
+  if (rc) return rc;
+  if (workspace_bytes < P.total) return fail(LRFB_E_WORKSPACE, "workspace %lld < %lld", (long long)workspace_bytes, P.total);
+  cudaStream_t st = (cudaStream_t)(uintptr_t)stream;
+  unsigned char* ws = reinterpret_cast<unsigned char*>(d_workspace);
+  if (cudaMemsetAsync(ws + P.off_counter, 0, 64, st) != cudaSuccess) return fail(LRFB_E_ARG, "memset failed");
+  for (int g = 0; g < P.n_groups; ++g) {
+    d9::Params K;
+    memset(&K, 0, sizeof(K));
+    K.rec = reinterpret_cast<const unsigned char*>(d_records), K.rec_stride = P.L.record_bytes;
+    K.len = P.group_len[g], K.slot = (K.len + 16 + 15) & ~15;
+    for (int mtx = 0; mtx < P.n_mat; ++mtx)
+      if (P.len[mtx] == K.len) {
+        d9::ColSeg& sg = K.seg[K.n_seg++];
+        sg.rec_off = (int)P.rec_off[mtx], sg.ncols = P.ncols[mtx], sg.col0 = P.col0[mtx], sg.out_off = P.slot_off[mtx];
+        K.cols_per_image += P.ncols[mtx];
+      }
+    K.cols_total = P.cols_total, K.batch = batch;
+    K.cbuf = ws + P.off_cbuf, K.img_stride = P.img_stride;
+    K.csize = reinterpret_cast<unsigned*>(ws + P.off_csize);
+    K.scratch = ws + P.off_scratch;
+    K.counter = reinterpret_cast<int*>(ws + P.off_counter) + g;
+    const int smem = d9::smem_bytes(K.len);
+#ifndef LRFB_SIM
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(d9::deflate9_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return fail((int)e, "deflate9 shared memory %d: %s", smem, cudaGetErrorString(e));
+    }
+    cudaFuncSetAttribute(d9::deflate9_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+#endif
+    LRFB_LAUNCH(d9::deflate9_kernel, dim3(P.grid[g]), dim3(32), smem, st, K);
+    if ((rc = check_launch("deflate9_kernel"))) return rc;
+  }
+  d9::FrameParams F;
+  memset(&F, 0, sizeof(F));
+  F.n_mat = P.n_mat;
+  for (int mtx = 0; mtx < P.n_mat; ++mtx) {
+    F.ncols[mtx] = P.ncols[mtx], F.col0[mtx] = P.col0[mtx], F.slot_off[mtx] = P.slot_off[mtx], F.slot[mtx] = P.slot[mtx];
+    F.hdr_len[mtx] = snprintf(F.hdr[mtx], sizeof(F.hdr[mtx]), "{\"num_fibers\": %d, \"mode\": \"col\", \"dtype\": \"int8\"}", P.ncols[mtx]);
+  }
+  F.meta_len = (int)metadata_len;
+  memcpy(F.meta, metadata_json, (size_t)metadata_len);
+  F.cols_total = P.cols_total, F.batch = batch;
+  F.cbuf = ws + P.off_cbuf, F.img_stride = P.img_stride;
+  F.csize = reinterpret_cast<const unsigned*>(ws + P.off_csize);
+  F.sizes = reinterpret_cast<long long*>(ws + P.off_sizes);
+  F.offsets = reinterpret_cast<long long*>(d_offsets);
+  F.blob = d_blob, F.capacity = blob_capacity;
+  LRFB_LAUNCH(d9::frame_sizes_kernel, dim3((batch + 127) / 128), dim3(128), 0, st, F);
+  if ((rc = check_launch("frame_sizes_kernel"))) return rc;
+  LRFB_LAUNCH(d9::frame_scan_kernel, dim3(1), dim3(1024), 0, st, (const long long*)F.sizes, F.offsets, (int)batch);
+  if ((rc = check_launch("frame_scan_kernel"))) return rc;
+  LRFB_LAUNCH(d9::frame_write_kernel, dim3(batch), dim3(d9::kFrameThreads), 0, st, F);
+  return check_launch("frame_write_kernel");
+}
+
+#ifdef LRFB_SIM
+// test tooling (shim build only): the serial restatement, see deflate9.cuh
+LRFB_EXPORT int64_t lrfb_sim_deflate9_serial(const uint8_t* in, int32_t n, uint8_t* out) {
+  return d9::deflate9_serial(in, n, out, nullptr);
+}
+#endif
 
 LRFB_EXPORT int32_t lrfb_debug_set(const char* knob, int32_t value) {
   if (!knob) return fail(LRFB_E_ARG, "knob is null");

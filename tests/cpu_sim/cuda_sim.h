@@ -154,6 +154,34 @@ inline unsigned __ballot_sync(unsigned, bool pred) {
   return m;
 }
 inline int __ffs(int v) { return __builtin_ffs(v); }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
+inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) {
+  return (unsigned)((((unsigned long long)hi << 32) | lo) >> (sh & 31));
+}
+template <class T>
+inline T __shfl_up_sync(unsigned, T v, int delta, int width = 32) {
+  int lane = sim::ctx.lin & 31;
+  int src = lane - delta;
+  if (src < (lane & ~(width - 1))) src = lane;
+  return sim::exchange(v, src);
+}
+inline int __reduce_max_sync(unsigned, int v) {
+  for (int o = 16; o; o >>= 1) v = std::max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+inline unsigned __match_any_sync(unsigned, unsigned v) {
+  unsigned m = 0;
+  for (int l = 0; l < 32; ++l) {
+    unsigned got = __shfl_sync(0xffffffffu, v, l);
+    int n = sim::ctx.blk->nthreads - (sim::ctx.lin & ~31);
+    if (l < n && got == v) m |= 1u << l;
+  }
+  return m;
+}
+inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+template <class T> inline T __ldcg(const T* p) { return *p; }
+template <class T> inline void __stcg(T* p, T v) { *p = v; }
 inline int __reduce_add_sync(unsigned, int v) {
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;

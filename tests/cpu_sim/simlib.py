@@ -159,3 +159,27 @@ def svd_decode(codes: np.ndarray, qp6: np.ndarray, cfg):
     qp6 = np.ascontiguousarray(qp6, np.float32)
     _cabi.check(lib().lrfb_svd_decode(C.byref(cfg), B, _ptr(codes), _ptr(qp6), _ptr(out), None), "svd_decode", lib())
     return out
+
+
+def pack_device(records: np.ndarray, cfg, meta: bytes):
+    """lrfb_qmf_pack_device on the shim: records (B, record_bytes) int8 -> list of framed byte strings."""
+    records = np.ascontiguousarray(records, np.int8)
+    B = records.shape[0]
+    wsb = lib().lrfb_qmf_pack_device_workspace(C.byref(cfg), B)
+    assert wsb > 0, lib().lrfb_last_error()
+    ws = np.zeros(wsb + 256, np.uint8)
+    cap = B * lib().lrfb_qmf_pack_bound(C.byref(cfg), len(meta))
+    blob = np.zeros(cap, np.uint8)
+    offs = np.zeros(B + 1, np.int64)
+    rc = lib().lrfb_qmf_pack_device(C.byref(cfg), B, _ptr(records), meta, len(meta), _ptr(blob), cap, _ptr(offs),
+                                    _ptr(ws), wsb, None)
+    _cabi.check(rc, "pack_device", lib())
+    return [blob[offs[i]:offs[i + 1]].tobytes() for i in range(B)]
+
+
+def deflate9_serial(data: bytes) -> bytes:
+    fn = lib().lrfb_sim_deflate9_serial
+    fn.restype, fn.argtypes = C.c_int64, [C.c_char_p, C.c_int32, C.c_void_p]
+    out = np.zeros(len(data) + 64, np.uint8)
+    n = fn(data, len(data), _ptr(out))
+    return out[:n].tobytes()

@@ -1,0 +1,105 @@
+"""The device lossless stage (lrf_b200/csrc/deflate9.cuh) against zlib itself, byte for byte.
+
+CPU part: the serial restatement (shim build only) on thousands of streams — it shares the Huffman-tree, block-choice
+and header code with the kernel — and the kernel proper (warp-parallel chain walk, sort, parallel symbol coding,
+framing kernels) on the SIMT shim for small records.  GPU part: lrfb_qmf_pack_device against packing.pack_qmf_record
+(Python zlib) on real factor records and on adversarial ones."""
+import ctypes as C
+import zlib
+
+import numpy as np
+import pytest
+import torch
+
+from lrf_b200 import _cabi, compression, packing
+
+
+def _streams(rng, count, max_len):
+    out = []
+    for it in range(count):
+        n = int(rng.integers(0, 70)) if it % 5 == 0 else 64 if it % 5 == 1 else int(rng.integers(0, max_len))
+        mode = it % 7
+        if mode == 0:
+            a = rng.integers(0, 256, n)
+        elif mode == 1:
+            a = rng.integers(-16, 16, n)
+        elif mode == 2:
+            a = np.clip(np.cumsum(rng.integers(-1, 2, n)), -16, 15)
+        elif mode == 3:
+            a = np.where((np.arange(n) // 50) % 3 > 0, 0, rng.integers(0, 4, n))
+        elif mode == 4:
+            a = np.rint(8 * np.sin(np.arange(n) * 0.01 * (1 + it % 5))) + (rng.integers(0, 3, n) == 0)
+        elif mode == 5:
+            a = np.zeros(n)
+        else:
+            base = rng.integers(-4, 5, 100)
+            a = base[np.arange(n) % 100] + (rng.integers(0, 20, n) == 0)
+        out.append(a.astype(np.int8).tobytes())
+    return out
+
+
+def test_serial_restatement_matches_zlib():
+    from cpu_sim import simlib
+
+    rng = np.random.default_rng(11)
+    for data in _streams(rng, 1500, 9000) + [bytes(16382), rng.integers(-16, 16, 16382).astype(np.int8).tobytes()]:
+        assert simlib.deflate9_serial(data) == zlib.compress(data, 9), len(data)
+
+
+def _records(rng, lay, count):
+    recs = rng.integers(-16, 16, size=(count, lay.record_bytes)).astype(np.int8)
+    recs[0] = 0
+    if count > 1:
+        recs[1, ::2] = 15
+    if count > 2:  # smooth columns: long matches, long hash chains
+        t = np.arange(lay.record_bytes)
+        recs[2] = np.rint(10 * np.sin(t * 0.02) + 3 * np.sin(t * 0.11)).astype(np.int8)
+    if count > 3:
+        recs[3] = np.clip(np.cumsum(rng.integers(-1, 2, lay.record_bytes)), -16, 15).astype(np.int8)
+    return recs
+
+
+@pytest.mark.parametrize("shape,quality", [((48, 64), 7), ((96, 160), 25)])
+def test_kernel_on_shim_matches_python_packer(shape, quality):
+    from cpu_sim import simlib
+
+    H, W = shape
+    cfg, lay = compression.resolve_plan(H, W, None, quality, "YCbCr", (0.5, 0.5), (8, 8), (-16, 15), 10)
+    meta = compression._metadata(torch.uint8, "YCbCr", True, (-16, 15), (8, 8), lay)
+    recs = _records(np.random.default_rng(5), lay, 5)
+    want = [packing.pack_qmf_record(recs[i], lay, meta) for i in range(len(recs))]
+    got = simlib.pack_device(recs, cfg, packing.dict_to_bytes(meta))
+    assert got == want
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,quality,batch", [((512, 768), 7, 24), ((96, 160), 25, 33), ((200, 328), 3, 7)])
+def test_device_packer_matches_python_packer(shape, quality, batch):
+    H, W = shape
+    cfg, lay = compression.resolve_plan(H, W, None, quality, "YCbCr", (0.5, 0.5), (8, 8), (-16, 15), 10)
+    meta = compression._metadata(torch.uint8, "YCbCr", True, (-16, 15), (8, 8), lay)
+    recs = _records(np.random.default_rng(7), lay, batch)
+    want = [packing.pack_qmf_record(recs[i], lay, meta) for i in range(batch)]
+    got = compression.pack_records_device(torch.from_numpy(recs).cuda(), cfg, lay, meta)
+    assert got == want
+
+
+@pytest.mark.gpu
+def test_device_packer_on_real_factors_and_public_api():
+    """qmf_encode_batch goes through the device packer; its bytes equal the host packers' on real factors."""
+    from oracle import qmf_port as port
+
+    imgs = torch.stack([port.s_nat(1000 + i, 256, 384) for i in range(6)])
+    records, lay, meta = compression.qmf_encode_batch(imgs, quality=7, return_records=True)
+    cfg, _ = compression.resolve_plan(256, 384, None, 7, "YCbCr", (0.5, 0.5), (8, 8), (-16, 15), 10)
+    host = records.cpu().numpy()
+    want = [packing.pack_qmf_record(host[i], lay, meta) for i in range(len(host))]
+    assert compression.pack_records_device(records, cfg, lay, meta) == want
+    assert compression.pack_records(host, cfg, lay, meta) == want
+    assert compression.qmf_encode_batch(imgs, quality=7) == want
+
+
+@pytest.mark.gpu
+def test_device_packer_refuses_long_columns():
+    cfg, lay = compression.resolve_plan(1365, 2048, None, 7, "YCbCr", (0.5, 0.5), (8, 8), (-16, 15), 10)
+    assert _cabi.lib().lrfb_qmf_pack_device_workspace(C.byref(cfg), 4) == -1
