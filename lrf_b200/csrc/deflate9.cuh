@@ -374,7 +374,7 @@ struct Params {
   int* counter;             // work queue, zeroed before the launch
 };
 __host__ __device__ inline int pad_len(int len) { return (len + 63) & ~63; }
-__host__ __device__ inline long long scratch_per_cta(int len) { return 5ll * pad_len(len); }
+__host__ __device__ inline long long scratch_per_cta(int len) { return 7ll * pad_len(len); }
 __host__ __device__ inline int smem_data(int len) { return (len + 16 + 15) & ~15; }
 constexpr int kFreqPad = (kFreqBytes + 15) & ~15, kCntBytes = 2 * (256 + 128), kTreePad = (kTreeBytes + 15) & ~15;
 __host__ __device__ inline int smem_region(int len) {
@@ -407,9 +407,10 @@ __global__ void __launch_bounds__(32) deflate9_kernel(Params P) {
   unsigned char* region = freq_mem + kFreqPad + kCntBytes;
   unsigned short* A = reinterpret_cast<unsigned short*>(region);  // positions sorted by (hash, position)
   unsigned char* scr = P.scratch + (long long)blockIdx.x * scratch_per_cta(n);
-  unsigned short* B = reinterpret_cast<unsigned short*>(scr);                // sort ping-pong, then rank[position]
-  unsigned short* sym_d = reinterpret_cast<unsigned short*>(scr + 2 * lp);   // match distance, 0 = literal
-  unsigned char* sym_l = scr + 4 * lp;                                       // literal byte / match length - 3
+  unsigned short* B = reinterpret_cast<unsigned short*>(scr);                // sort ping-pong, dead once RC is written
+  unsigned* RC = reinterpret_cast<unsigned*>(scr);                           // per position: rank | chain candidates << 16
+  unsigned short* sym_d = reinterpret_cast<unsigned short*>(scr + 4 * lp);   // match distance, 0 = literal
+  unsigned char* sym_l = scr + 6 * lp;                                       // literal byte / match length - 3
   const int n_streams = P.batch * P.cols_per_image;
 
   for (;;) {
@@ -491,7 +492,33 @@ __global__ void __launch_bounds__(32) deflate9_kernel(Params P) {
         __syncwarp();
       }
     }
-    for (int k = lane; k < m; k += 32) __stcg(B + A[k], (unsigned short)k);  // rank of every position
+    {  // per position: its rank in A and the number of chain candidates below it (same hash, position 0 excluded: NIL)
+      int run_start = 0, kzero = -1, carry_h = -1;
+      for (int base = 0; base < m; base += 32) {
+        const int k = base + lane;
+        const bool valid = k < m;
+        const int q = valid ? A[k] : 0;
+        const int hk = valid ? (int)hash3(data, q) : -2;
+        int hp = __shfl_up_sync(0xffffffffu, hk, 1);
+        if (lane == 0) hp = carry_h;
+        carry_h = __shfl_sync(0xffffffffu, hk, 31);
+        const unsigned zb = __ballot_sync(0xffffffffu, valid && q == 0);
+        if (zb) kzero = base + __ffs((int)zb) - 1;
+        int st = (valid && hk != hp) ? k : -1;  // bucket starts, then an inclusive max-scan
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, st, o);
+          if (lane >= o) st = st > t ? st : t;
+        }
+        if (st < 0) st = run_start;
+        run_start = __shfl_sync(0xffffffffu, st, 31);
+        if (valid) {
+          int cl = k - st - (st == kzero ? 1 : 0);
+          if (cl < 0) cl = 0;
+          __stcg(RC + q, (unsigned)k | ((unsigned)cl << 16));
+        }
+      }
+    }
     __syncwarp();
 
     // ---- deflate_slow ------------------------------------------------------------------------------------------------
@@ -499,7 +526,7 @@ __global__ void __launch_bounds__(32) deflate9_kernel(Params P) {
     unsigned short* dfreq = lfreq + kHeap;
     int strstart = 0, lookahead = n, match_length = 2, match_start = 0, match_available = 0, ns = 0;
     int wbase = -1000000;
-    int rk_cur = 0, rk_nxt = 0;
+    unsigned rk_cur = 0, rk_nxt = 0;
     while (lookahead > 0) {
       const int prev_length = match_length, prev_match = match_start;
       match_length = 2;
@@ -508,49 +535,49 @@ __global__ void __launch_bounds__(32) deflate9_kernel(Params P) {
         const int p = strstart;
         if (p < wbase || p - wbase >= 64) {
           wbase = p & ~31;
-          rk_cur = (wbase + lane < m) ? __ldcg(B + wbase + lane) : 0;
-          rk_nxt = (wbase + 32 + lane < m) ? __ldcg(B + wbase + 32 + lane) : 0;
+          rk_cur = (wbase + lane < m) ? __ldcg(RC + wbase + lane) : 0u;
+          rk_nxt = (wbase + 32 + lane < m) ? __ldcg(RC + wbase + 32 + lane) : 0u;
         } else if (p - wbase >= 32) {
           wbase += 32;
           rk_cur = rk_nxt;
-          rk_nxt = (wbase + 32 + lane < m) ? __ldcg(B + wbase + 32 + lane) : 0;
+          rk_nxt = (wbase + 32 + lane < m) ? __ldcg(RC + wbase + 32 + lane) : 0u;
         }
-        const int r = __shfl_sync(0xffffffffu, rk_cur, p - wbase);
-        const unsigned h = hash3(data, p);
+        const unsigned rc = __shfl_sync(0xffffffffu, rk_cur, p - wbase);
         int best = prev_length, bpos = match_start;
-        int chain = prev_length >= 32 ? 1024 : 4096;
-        for (int k = r - 1; chain > 0 && k >= 0; k -= 32, chain -= 32) {
-          const int idx = k - lane;
+        // zlib walks at most max_chain (4096; a quarter once the previous match is >= good_length) candidates, newest
+        // first; here they are A[r-1], A[r-2], ... and 32 of them are tested per step
+        int left = (int)(rc >> 16);
+        {
+          const int chain = prev_length >= 32 ? 1024 : 4096;
+          left = left < chain ? left : chain;
+        }
+        unsigned pb = data[p + best], pb1 = data[p + best - 1];
+        for (int k = (int)(rc & 0xffffu) - 1 - lane; left > 0; k -= 32, left -= 32) {
+          unsigned key = 0;
           int q = 0;
-          bool valid = false;
-          if (idx >= 0) {
-            q = A[idx];
-            valid = q != 0 && hash3(data, q) == h;
-          }
-          const unsigned vm = __ballot_sync(0xffffffffu, valid);
-          if (!vm) break;
-          int len = 0;
-          if (valid && data[q + best] == data[p + best] && data[q + best - 1] == data[p + best - 1]) {
-            while (len < maxlen) {
-              const unsigned x = ld4(data32, p + len) ^ ld4(data32, q + len);
-              if (x) {
-                len += (__ffs((int)x) - 1) >> 3;
-                break;
+          if (lane < left) {
+            q = A[k];
+            if (data[q + best] == pb && data[q + best - 1] == pb1) {
+              int len = 0;
+              while (len < maxlen) {
+                const unsigned x = ld4(data32, p + len) ^ ld4(data32, q + len);
+                if (x) {
+                  len += (__ffs((int)x) - 1) >> 3;
+                  break;
+                }
+                len += 4;
               }
-              len += 4;
+              if (len > maxlen) len = maxlen;
+              if (len > best) key = ((unsigned)len << 5) | (unsigned)(31 - lane);  // longest, then closest
             }
-            if (len > maxlen) len = maxlen;
           }
-          const unsigned nm = __ballot_sync(0xffffffffu, len >= maxlen);
-          const unsigned consider = nm ? ((2u << (__ffs((int)nm) - 1)) - 1u) : 0xffffffffu;
-          const int lc = ((consider >> lane) & 1u) ? len : 0;
-          const int mx = __reduce_max_sync(0xffffffffu, lc);
-          if (mx > best) {
-            const unsigned who = __ballot_sync(0xffffffffu, lc == mx);
-            bpos = __shfl_sync(0xffffffffu, q, __ffs((int)who) - 1);
-            best = mx;
+          const unsigned mx = __reduce_max_sync(0xffffffffu, key);
+          if (mx) {
+            best = (int)(mx >> 5);
+            bpos = __shfl_sync(0xffffffffu, q, 31 - (int)(mx & 31u));
+            if (best >= maxlen) break;  // nice_length (or the end of the input) reached: zlib stops at the first such candidate
+            pb = data[p + best], pb1 = data[p + best - 1];
           }
-          if (nm || vm != 0xffffffffu) break;
         }
         match_length = best;
         match_start = bpos;
