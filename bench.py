@@ -299,6 +299,31 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = mpix_step / float(te.item())
     same = bool(torch.equal(h_out, plan.factors.cpu()))
+
+    # ---- the same call ending in the reference's `bytes`: device deflate behind every chunk, only the streams come back --
+    from lrf_b200 import packing as _packing
+
+    meta_json = _packing.dict_to_bytes(compression._metadata(torch.uint8, "YCbCr", True, KW["bounds"], KW["patch_size"], lay))
+    blob_cap = B * int(lib.lrfb_qmf_pack_bound(C.byref(cfg), len(meta_json)))
+    h_blob = torch.empty(blob_cap, dtype=torch.uint8, pin_memory=True)
+    h_offs = torch.zeros(B + 1, dtype=torch.int64, pin_memory=True)
+
+    def e2e_bytes_step():
+        _cabi.check(lib.lrfb_qmf_encode_bytes_host(ctx, C.byref(cfg), B, C.c_void_p(h_in.data_ptr()), meta_json, len(meta_json),
+                                                   C.c_void_p(h_blob.data_ptr()), blob_cap, C.c_void_p(h_offs.data_ptr())),
+                    "lrfb_qmf_encode_bytes_host")
+
+    e2e_bytes_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_bytes_step()  # synchronous: returns when every stream is in host memory
+    barrier()
+    tb = torch.tensor([(time.perf_counter() - t0) / args.e2e_steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+    e2e_bytes_value = mpix_step / float(tb.item())
+    e2e_blob_bytes = int(h_offs[B].item())
     lib.lrfb_ctx_destroy(ctx)
 
     # ---- plain concurrent H2D copy of the same bytes: the machine's ceiling for `e2e` (PCIe / host memory) ----------
@@ -414,7 +439,33 @@ def main():
     stats = gather_stats(stats, n_s * world, rank, world).cpu()  # the only collective (NCCL all_gather)
     psnr_host = psnr[:n_s].cpu()
 
-    # ---- end to end to `bytes`: host uint8 images -> H2D -> kernels -> D2H -> native zlib pool -> list[bytes] -----
+    # the streams the bytes-ending e2e call left in host memory against the host packer's on the same images
+    ho = h_offs.numpy()
+    hb = memoryview(h_blob.numpy())
+    bytes_equal = all(bytes(hb[ho[i]: ho[i + 1]]) == blobs[i] for i in range(n_s))
+
+    # ---- lossless stage alone, device resident: records of the step above -> framed zlib-9 streams ---------------------
+    pws = int(lib.lrfb_qmf_pack_device_workspace(C.byref(cfg), B))
+    d_pws = torch.empty(pws, dtype=torch.uint8, device=dev)
+    d_blob = torch.empty(blob_cap, dtype=torch.uint8, device=dev)
+    d_offs = torch.empty(B + 1, dtype=torch.int64, device=dev)
+
+    def pack_only():
+        _cabi.check(lib.lrfb_qmf_pack_device(C.byref(cfg), B, C.c_void_p(plan.factors.data_ptr()), meta_json, len(meta_json),
+                                             C.c_void_p(d_blob.data_ptr()), blob_cap, C.c_void_p(d_offs.data_ptr()),
+                                             C.c_void_p(d_pws.data_ptr()), pws, C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                    "lrfb_qmf_pack_device")
+
+    barrier()
+    pms = allmax(time_steps_ms(pack_only, 2, 3))
+    extras["pack"] = {"value": mpix_step / (pms / 1e3), "unit": "Mpixel/s", "ms_per_step": pms,
+                      "workload": "lrfb_qmf_pack_device on the %d records per GPU of the encode above: zlib level 9 per factor "
+                                  "column (one warp each) + framing, byte-identical to the host packer" % B,
+                      "factor_bytes_in": int(plan.factors.numel()), "stream_bytes_out": int(d_offs[B].item()),
+                      "vs_host_packer": (mpix_step / world / (pms / 1e3)) / (n_s * H * W / 1e6 / pack_s)}
+    del d_pws, d_blob, d_offs
+
+    # ---- end to end to `bytes` through the Python API: pinned host uint8 images -> list[bytes] -------------------------
     if not args.quick:
         n_b = min(B, args.bytes_images)
         lrf_b200.qmf_encode_batch(h_in[:64], **KW)
@@ -423,8 +474,8 @@ def main():
         out_b = lrf_b200.qmf_encode_batch(h_in[:n_b], **KW)
         tb = allmax(time.perf_counter() - t0)
         extras["e2e_bytes"] = {"value": world * n_b * H * W / 1e6 / tb, "unit": "Mpixel/s", "images_per_gpu": n_b,
-                               "call": "lrf_b200.qmf_encode_batch(host uint8 images) -> list[bytes] "
-                                       "(H2D, kernels, D2H, zlib level 9 on %d host threads, bytes objects)" % (os.cpu_count() or 1),
+                               "call": "lrf_b200.qmf_encode_batch(pinned host uint8 images) -> list[bytes] "
+                                       "(lrfb_qmf_encode_bytes_host + one bytes object per image)",
                                "seconds": tb, "bytes_equal_sample_pack": out_b[:n_s] == blobs[:min(n_s, n_b)]}
         del out_b
 
@@ -512,15 +563,20 @@ def main():
                        "batch_per_gpu": B, "distinct_images": POOL, "generator": "s_nat(seed=1000+i) SURVEY §8d",
                        "l2": "inputs %.1f GB per GPU >> 126 MB L2, no flush needed" % (B * 3 * H * W / 1e9),
                        "sharding": "images split across ranks, no data-path collective"},
-            "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": int(h_in.numel()) * world,
-                    "d2h_bytes_per_step": int(h_out.numel()) * world, "records_equal_device_path": same,
-                    "call": "lrfb_qmf_encode_host (C ABI, pinned host buffers); stops at int8 factor records in host "
-                            "memory - see e2e_bytes for the run that ends in `bytes`",
+            "e2e": {"value": e2e_bytes_value, "unit": "Mpixel/s", "h2d_bytes_per_step": int(h_in.numel()) * world,
+                    "d2h_bytes_per_step": (e2e_blob_bytes + 8 * (B + 1)) * world,
+                    "streams_equal_host_packer_sample": bytes_equal,
+                    "call": "lrfb_qmf_encode_bytes_host (C ABI, pinned host buffers): host images -> the reference's "
+                            "encoded byte streams in host memory (H2D, encode kernels, device zlib-9 deflate + framing, "
+                            "D2H of the streams) - the same end point as the CPU arm, which includes zlib",
                     "host_affinity": affinity,
+                    "records_only": {"value": e2e_value, "unit": "Mpixel/s", "d2h_bytes_per_step": int(h_out.numel()) * world,
+                                     "records_equal_device_path": same,
+                                     "call": "lrfb_qmf_encode_host: stops at the int8 factor records in host memory"},
                     "h2d_ceiling": {"value": e2e_ceiling, "unit": "Mpixel/s", "gbs_per_gpu": h2d_gbs_per_gpu,
                                     "what": "the same pinned input copied to the device by plain concurrent "
                                             "cudaMemcpyAsync on every rank, nothing else running",
-                                    "frac_of_ceiling": e2e_value / e2e_ceiling}},
+                                    "frac_of_ceiling": e2e_bytes_value / e2e_ceiling}},
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
             "roofline": roofline,

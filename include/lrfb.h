@@ -201,6 +201,15 @@ int32_t lrfb_qmf_pack_device(const lrfb_qmf_config* cfg, int32_t batch, const in
                              const char* metadata_json, int64_t metadata_len, uint8_t* d_blob, int64_t blob_capacity,
                              int64_t* d_offsets, void* d_workspace, int64_t workspace_bytes, void* stream);
 
+/* The whole of lrf.qmf_encode for a batch with HOST buffers (lrf/compression/qmf.py:116-292): images in, finished byte
+ * streams out.  The chunked pipeline of lrfb_qmf_encode_host with lrfb_qmf_pack_device behind every chunk; only the
+ * compressed streams cross PCIe on the way back.  Image i's stream is h_blob[h_offsets[i] .. h_offsets[i+1]);
+ * h_offsets has batch + 1 entries; blob_capacity >= batch * lrfb_qmf_pack_bound always suffices (LRFB_E_WORKSPACE
+ * otherwise); h_images and h_blob should be pinned.  Same shape limits as lrfb_qmf_pack_device. */
+int32_t lrfb_qmf_encode_bytes_host(lrfb_ctx* ctx, const lrfb_qmf_config* cfg, int32_t batch, const void* h_images,
+                                   const char* metadata_json, int64_t metadata_len, uint8_t* h_blob,
+                                   int64_t blob_capacity, int64_t* h_offsets);
+
 /* Test hook: select a kernel variant process-wide.  Knobs: "decode_v1" (1 = per-row float decoder instead of the
  * int8 dot-product one).  The shipped library reads no environment variables. */
 int32_t lrfb_debug_set(const char* knob, int32_t value);

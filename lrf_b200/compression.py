@@ -87,6 +87,47 @@ def pack_records_device(records: torch.Tensor, cfg, lay, meta: dict) -> list[byt
     return [bytes(mv[o[i] : o[i + 1]]) for i in range(B)]
 
 
+class _HostPipe:
+    """Per-device context of the host-buffer C-ABI calls plus grow-only pinned output buffers."""
+
+    def __init__(self, index: int):
+        self.ctx = C.c_void_p()
+        _cabi.check(_cabi.lib().lrfb_ctx_create(index, C.byref(self.ctx)), "lrfb_ctx_create")
+        self.blob = None
+        self.offsets = None
+
+    def buffers(self, cap: int, batch: int):
+        if self.blob is None or self.blob.numel() < cap:
+            self.blob = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+        if self.offsets is None or self.offsets.numel() < batch + 1:
+            self.offsets = torch.empty(batch + 1, dtype=torch.int64, pin_memory=True)
+        return self.blob, self.offsets
+
+
+_PIPES: dict[int, _HostPipe] = {}
+
+
+def encode_bytes_host(images: torch.Tensor, cfg, lay, meta: dict, device_index: Optional[int] = None) -> list[bytes]:
+    """Host images (B,3,H,W) -> B encoded ``bytes`` through ``lrfb_qmf_encode_bytes_host``: chunked H2D | encode kernels |
+    device deflate | D2H of the finished streams.  ``images`` should be pinned for full copy bandwidth."""
+    assert not images.is_cuda and images.is_contiguous()
+    index = torch.cuda.current_device() if device_index is None else device_index
+    pipe = _PIPES.get(index)
+    if pipe is None:
+        pipe = _PIPES[index] = _HostPipe(index)
+    B = images.shape[0]
+    mj = packing.dict_to_bytes(meta)
+    lib = _cabi.lib()
+    cap = B * int(lib.lrfb_qmf_pack_bound(C.byref(cfg), len(mj)))
+    blob, offs = pipe.buffers(cap, B)
+    rc = lib.lrfb_qmf_encode_bytes_host(pipe.ctx, C.byref(cfg), B, C.c_void_p(images.data_ptr()), mj, len(mj),
+                                        C.c_void_p(blob.data_ptr()), blob.numel(), C.c_void_p(offs.data_ptr()))
+    _cabi.check(rc, "lrfb_qmf_encode_bytes_host")
+    o = offs.numpy()
+    mv = memoryview(blob.numpy())
+    return [bytes(mv[o[i] : o[i + 1]]) for i in range(B)]
+
+
 def _require_cuda() -> None:
     if not torch.cuda.is_available():
         raise _cabi.LrfbError("lrf_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
@@ -226,8 +267,16 @@ def qmf_encode_batch(images: torch.Tensor, rank=None, quality=None, color_space:
         assert not return_records, "patch=False factors are not stored as patch records"
         return _qmf_encode_nopatch(images, rank, quality, color_space, scale_factor, bounds, kwargs.get("num_iters", 10))
     device = images.device if images.is_cuda else torch.device("cuda", torch.cuda.current_device())
-    dev_images, in_dtype = _to_device_images(images, device)
     B, _, H, W = images.shape
+    if (not images.is_cuda and not return_records and images.is_pinned() and images.is_contiguous()
+            and images.dtype in (torch.uint8, torch.float32)):
+        in_dtype = _cabi.LRFB_U8 if images.dtype == torch.uint8 else _cabi.LRFB_F32
+        cfg, lay = resolve_plan(H, W, rank, quality, color_space, scale_factor, patch_size, bounds,
+                                kwargs.get("num_iters", 10), in_dtype)
+        if device_packer_supported(cfg, B):  # pinned host batch: the chunked host pipeline ends in bytes
+            meta = _metadata(images.dtype, color_space, patch, bounds, patch_size, lay)
+            return encode_bytes_host(images, cfg, lay, meta, device.index)
+    dev_images, in_dtype = _to_device_images(images, device)
     cfg, lay = resolve_plan(H, W, rank, quality, color_space, scale_factor, patch_size, bounds,
                             kwargs.get("num_iters", 10), in_dtype)
     with torch.cuda.device(device):

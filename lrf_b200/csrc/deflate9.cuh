@@ -383,6 +383,7 @@ __host__ __device__ inline int smem_region(int len) {
 }
 __host__ __device__ inline int smem_bytes(int len) { return smem_data(len) + kFreqPad + kCntBytes + smem_region(len); }
 
+constexpr int kWide = 4;  // chain candidates per lane and step
 __device__ __forceinline__ unsigned ld4(const unsigned* w, int off) {
   const int i = off >> 2;
   return __funnelshift_r(w[i], w[i + 1], (off & 3) * 8);
@@ -396,7 +397,7 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
   return v;
 }
 
-__global__ void __launch_bounds__(32) deflate9_kernel(Params P) {
+__global__ void __launch_bounds__(32, 16) deflate9_kernel(Params P) {
   LRFB_DYN_SMEM(smem);
   const int lane = threadIdx.x;
   const int n = P.len, m = n >= 3 ? n - 2 : 0, lp = pad_len(n);
@@ -551,32 +552,62 @@ __global__ void __launch_bounds__(32) deflate9_kernel(Params P) {
           const int chain = prev_length >= 32 ? 1024 : 4096;
           left = left < chain ? left : chain;
         }
-        unsigned pb = data[p + best], pb1 = data[p + best - 1];
-        for (int k = (int)(rc & 0xffffu) - 1 - lane; left > 0; k -= 32, left -= 32) {
-          unsigned key = 0;
-          int q = 0;
-          if (lane < left) {
-            q = A[k];
-            if (data[q + best] == pb && data[q + best - 1] == pb1) {
-              int len = 0;
-              while (len < maxlen) {
-                const unsigned x = ld4(data32, p + len) ^ ld4(data32, q + len);
-                if (x) {
-                  len += (__ffs((int)x) - 1) >> 3;
+        // A candidate can only beat `best` if it agrees with the string at p on bytes 0..best.  Filter on eight of them:
+        // best-3..best (what zlib's own quick check looks at, twice as wide) and 3..6 (right after the hashed
+        // trigram, where most chain members of these smooth columns part ways): ~3 % of the candidates get through.
+        unsigned pe, pem, ps, psm;
+        auto set_filter = [&]() {
+          pe = ld4(data32, p + best - 3), pem = best == 2 ? 0xffffff00u : 0xffffffffu;
+          const int c = best - 2 < 4 ? best - 2 : 4;
+          ps = ld4(data32, p + 3), psm = c >= 4 ? 0xffffffffu : (1u << (8 * c)) - 1u;
+        };
+        auto filter = [&](int q) {
+          return (((ld4(data32, q + best - 3) ^ pe) & pem) | ((ld4(data32, q + 3) ^ ps) & psm)) == 0u;
+        };
+        if (left > 0) set_filter();
+        bool done = false;
+        for (int k = (int)(rc & 0xffffu) - 1 - lane; left > 0 && !done; k -= 32 * kWide, left -= 32 * kWide) {
+          // kWide x 32 candidates per step (order index j * 32 + lane): their loads overlap
+          int q[kWide];
+          unsigned pm[kWide];
+#pragma unroll
+          for (int j = 0; j < kWide; ++j) q[j] = (32 * j + lane < left) ? A[k - 32 * j] : 0;
+#pragma unroll
+          for (int j = 0; j < kWide; ++j) pm[j] = __ballot_sync(0xffffffffu, q[j] != 0 && filter(q[j]));
+#pragma unroll
+          for (int j = 0; j < kWide; ++j) {
+            unsigned mset = pm[j];
+            while (mset) {  // the survivors in chain order, each compared by the whole warp (128 bytes per round)
+              const int src = __ffs((int)mset) - 1;
+              mset &= mset - 1;
+              const int qq = __shfl_sync(0xffffffffu, q[j], src);
+              int len = maxlen;
+              for (int base = 0; base < maxlen; base += 128) {
+                const int off = base + 4 * lane, nv = maxlen - off;
+                unsigned x = 0;
+                if (nv > 0) {
+                  x = ld4(data32, p + off) ^ ld4(data32, qq + off);
+                  if (nv < 4) x &= (1u << (8 * nv)) - 1u;
+                }
+                const int mn = __reduce_min_sync(0xffffffffu, x ? off + ((__ffs((int)x) - 1) >> 3) : 0x7fff);
+                if (mn != 0x7fff) {
+                  len = mn;
                   break;
                 }
-                len += 4;
               }
-              if (len > maxlen) len = maxlen;
-              if (len > best) key = ((unsigned)len << 5) | (unsigned)(31 - lane);  // longest, then closest
+              if (len > best) {
+                best = len, bpos = qq;
+                if (best >= maxlen) {  // nice_length (or the end of the input): zlib stops at the first such candidate
+                  done = true;
+                  break;
+                }
+                set_filter();  // the rest of this step is re-filtered against the new best
+                mset = __ballot_sync(0xffffffffu, lane > src && q[j] != 0 && filter(q[j]));
+#pragma unroll
+                for (int j2 = j + 1; j2 < kWide; ++j2) pm[j2] = __ballot_sync(0xffffffffu, q[j2] != 0 && filter(q[j2]));
+              }
             }
-          }
-          const unsigned mx = __reduce_max_sync(0xffffffffu, key);
-          if (mx) {
-            best = (int)(mx >> 5);
-            bpos = __shfl_sync(0xffffffffu, q, 31 - (int)(mx & 31u));
-            if (best >= maxlen) break;  // nice_length (or the end of the input) reached: zlib stops at the first such candidate
-            pb = data[p + best], pb1 = data[p + best - 1];
+            if (done) break;
           }
         }
         match_length = best;

@@ -1110,9 +1110,16 @@ struct lrfb_ctx {
   void* d_ws;
   size_t in_cap, out_cap, ws_cap;
   size_t chunk_bytes;    // input bytes per pipeline chunk
+  // lrfb_qmf_encode_bytes_host: two blob slots + their offset tables, the packer's workspace, pinned offset staging
+  void* d_blob;
+  void* d_offs;
+  void* d_pws;
+  long long* h_offs;
+  size_t blob_cap, offs_cap, pws_cap, hoffs_cap;
 #ifndef LRFB_SIM
   cudaStream_t back;     // D2H
-  cudaEvent_t landed[kHostSlots], consumed[kHostSlots], encoded[2], drained[2];
+  cudaStream_t pack;     // lossless stage (overlaps the next chunk's encode kernels)
+  cudaEvent_t landed[kHostSlots], consumed[kHostSlots], encoded[2], drained[2], packed[2], sized[2];
 #endif
 };
 
@@ -1139,7 +1146,7 @@ LRFB_EXPORT int32_t lrfb_ctx_create(int32_t device, lrfb_ctx** out) {
 }
 LRFB_EXPORT void lrfb_ctx_destroy(lrfb_ctx* c) {
   if (!c) return;
-  free(c->d_in), free(c->d_out), free(c->d_ws);
+  free(c->d_in), free(c->d_out), free(c->d_ws), free(c->d_blob), free(c->d_offs), free(c->d_pws), free(c->h_offs);
   delete c;
 }
 #else
@@ -1177,6 +1184,7 @@ LRFB_EXPORT int32_t lrfb_ctx_create(int32_t device, lrfb_ctx** out) {
   e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->back, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->pack, cudaStreamNonBlocking);
   for (int i = 0; i < kHostSlots && e == cudaSuccess; ++i) {
     e = cudaEventCreateWithFlags(&c->landed[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->consumed[i], cudaEventDisableTiming);
@@ -1184,6 +1192,8 @@ LRFB_EXPORT int32_t lrfb_ctx_create(int32_t device, lrfb_ctx** out) {
   for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
     e = cudaEventCreateWithFlags(&c->encoded[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->drained[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->packed[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->sized[i], cudaEventDisableTiming);
   }
   if (e != cudaSuccess) {
     delete c;
@@ -1198,8 +1208,14 @@ LRFB_EXPORT void lrfb_ctx_destroy(lrfb_ctx* c) {
   if (c->d_in) cudaFree(c->d_in);
   if (c->d_out) cudaFree(c->d_out);
   if (c->d_ws) cudaFree(c->d_ws);
+  if (c->d_blob) cudaFree(c->d_blob);
+  if (c->d_offs) cudaFree(c->d_offs);
+  if (c->d_pws) cudaFree(c->d_pws);
+  if (c->h_offs) cudaFreeHost(c->h_offs);
   for (int i = 0; i < kHostSlots; ++i) cudaEventDestroy(c->landed[i]), cudaEventDestroy(c->consumed[i]);
-  for (int i = 0; i < 2; ++i) cudaEventDestroy(c->encoded[i]), cudaEventDestroy(c->drained[i]);
+  for (int i = 0; i < 2; ++i)
+    cudaEventDestroy(c->encoded[i]), cudaEventDestroy(c->drained[i]), cudaEventDestroy(c->packed[i]), cudaEventDestroy(c->sized[i]);
+  cudaStreamDestroy(c->pack);
   cudaStreamDestroy(c->back);
   cudaStreamDestroy(c->copy);
   cudaStreamDestroy(c->stream);
@@ -1563,6 +1579,122 @@ LRFB_EXPORT int32_t lrfb_qmf_pack_device(const lrfb_qmf_config* cfg, int32_t bat
   if ((rc = check_launch("frame_scan_kernel"))) return rc;
   LRFB_LAUNCH(d9::frame_write_kernel, dim3(batch), dim3(d9::kFrameThreads), 0, st, F);
   return check_launch("frame_write_kernel");
+}
+
+// Host images -> finished byte streams in host memory, the whole of lrf.qmf_encode for a batch: the chunked pipeline of
+// lrfb_qmf_encode_host with the lossless stage on the device behind every chunk (its own stream, so it overlaps the next
+// chunk's encode kernels), and only the compressed streams on the way back.  The size of a chunk's blob is known when its
+// offsets arrive, so the host trails the device by one chunk: A(i) = enqueue H2D, kernels, packer, offsets D2H;
+// B(i) = wait for the offsets, enqueue the blob D2H.  Order A0 A1 B0 A2 B1 ...
+LRFB_EXPORT int32_t lrfb_qmf_encode_bytes_host(lrfb_ctx* c, const lrfb_qmf_config* cfg, int32_t batch,
+                                               const void* h_images, const char* metadata_json, int64_t metadata_len,
+                                               uint8_t* h_blob, int64_t blob_capacity, int64_t* h_offsets) {
+  if (!c || !h_images || !metadata_json || !h_blob || !h_offsets || batch <= 0 || metadata_len <= 0)
+    return fail(LRFB_E_ARG, "bad arguments");
+  lrfb_qmf_workspace_map m, mt;
+  lrfb_qmf_layout L;
+  int rc;
+  if ((rc = lrfb_qmf_layout_query(cfg, &L))) return rc;
+  const size_t img_bytes = (size_t)3 * cfg->height * cfg->width * (cfg->input_dtype == LRFB_U8 ? 1 : 4);
+  const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)batch, c->chunk_bytes / std::max<size_t>(img_bytes, 1)));
+  if ((rc = lrfb_qmf_workspace_query(cfg, chunk, &m))) return rc;
+  int64_t ws_need = m.total_bytes;
+  if (batch % chunk) {
+    if ((rc = lrfb_qmf_workspace_query(cfg, batch % chunk, &mt))) return rc;
+    ws_need = std::max(ws_need, mt.total_bytes);
+  }
+  const int64_t pws_need = lrfb_qmf_pack_device_workspace(cfg, chunk);
+  if (pws_need <= 0) return LRFB_E_UNSUPPORTED;  // message set by the plan
+  const int64_t bound = lrfb_qmf_pack_bound(cfg, metadata_len);
+  const size_t slot_blob = ((size_t)chunk * bound + 255) & ~(size_t)255, slot_offs = ((size_t)(chunk + 1) * 8 + 255) & ~(size_t)255;
+#ifndef LRFB_SIM
+  cudaSetDevice(c->device);
+#endif
+  if ((rc = grow(&c->d_in, &c->in_cap, (size_t)kHostSlots * chunk * img_bytes))) return rc;
+  if ((rc = grow(&c->d_out, &c->out_cap, (size_t)2 * chunk * L.record_bytes))) return rc;
+  if ((rc = grow(&c->d_ws, &c->ws_cap, (size_t)ws_need))) return rc;
+  if ((rc = grow(&c->d_blob, &c->blob_cap, 2 * slot_blob))) return rc;
+  if ((rc = grow(&c->d_offs, &c->offs_cap, 2 * slot_offs))) return rc;
+  if ((rc = grow(&c->d_pws, &c->pws_cap, (size_t)pws_need))) return rc;
+  if (c->hoffs_cap < 2 * slot_offs) {
+#ifndef LRFB_SIM
+    if (c->h_offs) cudaFreeHost(c->h_offs);
+    c->h_offs = nullptr, c->hoffs_cap = 0;
+    cudaError_t e = cudaHostAlloc((void**)&c->h_offs, 2 * slot_offs, cudaHostAllocDefault);
+    if (e != cudaSuccess) return fail((int)e, "cudaHostAlloc: %s", cudaGetErrorString(e));
+#else
+    free(c->h_offs);
+    c->h_offs = (long long*)malloc(2 * slot_offs);
+#endif
+    c->hoffs_cap = 2 * slot_offs;
+  }
+  const unsigned char* src = reinterpret_cast<const unsigned char*>(h_images);
+  const int n_chunks = (batch + chunk - 1) / chunk;
+  int64_t written = 0;
+  h_offsets[0] = 0;
+  auto stage_b = [&](int idx) -> int {  // sizes of chunk idx are on the host: bring its blob back
+    const int i0 = idx * chunk, n = std::min(chunk, batch - i0), oslot = idx & 1;
+    const long long* ho = c->h_offs + (size_t)oslot * slot_offs / 8;
+#ifndef LRFB_SIM
+    cudaError_t e = cudaEventSynchronize(c->sized[oslot]);
+    if (e != cudaSuccess) return fail((int)e, "pipeline: %s", cudaGetErrorString(e));
+#endif
+    const int64_t total = ho[n];
+    if ((int64_t)slot_blob < total || written + total > blob_capacity)
+      return fail(LRFB_E_WORKSPACE, "blob_capacity %lld too small (chunk %d needs %lld more)", (long long)blob_capacity, idx, (long long)total);
+    for (int i = 0; i < n; ++i) h_offsets[i0 + i + 1] = written + ho[i + 1];
+    const unsigned char* d_blob = reinterpret_cast<const unsigned char*>(c->d_blob) + (size_t)oslot * slot_blob;
+#ifndef LRFB_SIM
+    int r = d2h(h_blob + written, d_blob, (size_t)total, c->back);
+    cudaEventRecord(c->drained[oslot], c->back);
+#else
+    int r = d2h(h_blob + written, d_blob, (size_t)total, c->stream);
+#endif
+    written += total;
+    return r;
+  };
+  for (int idx = 0; idx < n_chunks; ++idx) {
+    const int i0 = idx * chunk, n = std::min(chunk, batch - i0);
+    const int slot = idx % kHostSlots, oslot = idx & 1;
+    unsigned char* d_in = reinterpret_cast<unsigned char*>(c->d_in) + (size_t)slot * chunk * img_bytes;
+    int8_t* d_out = reinterpret_cast<int8_t*>(c->d_out) + (size_t)oslot * chunk * L.record_bytes;
+    uint8_t* d_blob = reinterpret_cast<uint8_t*>(c->d_blob) + (size_t)oslot * slot_blob;
+    int64_t* d_offs = reinterpret_cast<int64_t*>(reinterpret_cast<unsigned char*>(c->d_offs) + (size_t)oslot * slot_offs);
+    long long* ho = c->h_offs + (size_t)oslot * slot_offs / 8;
+#ifndef LRFB_SIM
+    if (idx >= kHostSlots) cudaStreamWaitEvent(c->copy, c->consumed[slot], 0);
+    if ((rc = h2d(d_in, src + (size_t)i0 * img_bytes, (size_t)n * img_bytes, c->copy))) return rc;
+    cudaEventRecord(c->landed[slot], c->copy);
+    cudaStreamWaitEvent(c->stream, c->landed[slot], 0);
+    if (idx >= 2) cudaStreamWaitEvent(c->stream, c->packed[oslot], 0);  // the packer of chunk idx-2 is done with d_out[oslot]
+    if ((rc = lrfb_qmf_encode(cfg, n, d_in, d_out, c->d_ws, (int64_t)c->ws_cap, nullptr, (void*)(uintptr_t)c->stream)))
+      return rc;
+    cudaEventRecord(c->consumed[slot], c->stream);
+    cudaEventRecord(c->encoded[oslot], c->stream);
+    cudaStreamWaitEvent(c->pack, c->encoded[oslot], 0);
+    if (idx >= 2) cudaStreamWaitEvent(c->pack, c->drained[oslot], 0);  // blob of chunk idx-2 has left d_blob[oslot] (B(idx-2) ran)
+    if ((rc = lrfb_qmf_pack_device(cfg, n, d_out, metadata_json, metadata_len, d_blob, (int64_t)slot_blob, d_offs, c->d_pws,
+                                   (int64_t)c->pws_cap, (void*)(uintptr_t)c->pack)))
+      return rc;
+    cudaEventRecord(c->packed[oslot], c->pack);
+    if ((rc = d2h(ho, d_offs, (size_t)(n + 1) * 8, c->pack))) return rc;
+    cudaEventRecord(c->sized[oslot], c->pack);
+#else
+    if ((rc = h2d(d_in, src + (size_t)i0 * img_bytes, (size_t)n * img_bytes, c->stream))) return rc;
+    if ((rc = lrfb_qmf_encode(cfg, n, d_in, d_out, c->d_ws, (int64_t)c->ws_cap, nullptr, nullptr))) return rc;
+    if ((rc = lrfb_qmf_pack_device(cfg, n, d_out, metadata_json, metadata_len, d_blob, (int64_t)slot_blob, d_offs, c->d_pws,
+                                   (int64_t)c->pws_cap, nullptr)))
+      return rc;
+    if ((rc = d2h(ho, d_offs, (size_t)(n + 1) * 8, c->stream))) return rc;
+#endif
+    if (idx >= 1 && (rc = stage_b(idx - 1))) return rc;
+  }
+  if ((rc = stage_b(n_chunks - 1))) return rc;
+#ifndef LRFB_SIM
+  if ((rc = sync_stream(c->back))) return rc;
+  if ((rc = sync_stream(c->pack))) return rc;
+#endif
+  return sync_stream(c->stream);
 }
 
 #ifdef LRFB_SIM

@@ -174,6 +174,10 @@ inline unsigned __reduce_max_sync(unsigned, unsigned v) {
   for (int o = 16; o; o >>= 1) v = std::max(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
+inline int __reduce_min_sync(unsigned, int v) {
+  for (int o = 16; o; o >>= 1) v = std::min(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
 inline unsigned __match_any_sync(unsigned, unsigned v) {
   unsigned m = 0;
   for (int l = 0; l < 32; ++l) {

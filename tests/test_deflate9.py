@@ -103,3 +103,39 @@ def test_device_packer_on_real_factors_and_public_api():
 def test_device_packer_refuses_long_columns():
     cfg, lay = compression.resolve_plan(1365, 2048, None, 7, "YCbCr", (0.5, 0.5), (8, 8), (-16, 15), 10)
     assert _cabi.lib().lrfb_qmf_pack_device_workspace(C.byref(cfg), 4) == -1
+
+
+@pytest.mark.gpu
+def test_encode_bytes_host_pipeline_ragged_chunks():
+    """lrfb_qmf_encode_bytes_host (pinned host images -> finished streams) over 5 chunks with a ragged tail equals
+    encode + Python packer per image; the public batch API takes the same route for pinned inputs."""
+    from oracle import qmf_port as port
+
+    H, W, B = 96, 160, 37
+    pool = torch.stack([port.s_nat(2000 + i, H, W) for i in range(5)])
+    imgs = pool[torch.arange(B) % 5].contiguous().pin_memory()
+    records, lay, meta = compression.qmf_encode_batch(imgs.cuda(), quality=12, return_records=True)
+    host = records.cpu().numpy()
+    want = [packing.pack_qmf_record(host[i], lay, meta) for i in range(B)]
+    cfg, _ = compression.resolve_plan(H, W, None, 12, "YCbCr", (0.5, 0.5), (8, 8), (-16, 15), 10)
+    lib = _cabi.lib()
+    ctx = C.c_void_p()
+    _cabi.check(lib.lrfb_ctx_create(0, C.byref(ctx)), "ctx")
+    try:
+        _cabi.check(lib.lrfb_ctx_set_chunk_bytes(ctx, 8 * 3 * H * W), "chunk")  # 8 images per chunk: 4 full + 5
+        mj = packing.dict_to_bytes(meta)
+        cap = B * int(lib.lrfb_qmf_pack_bound(C.byref(cfg), len(mj)))
+        blob = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+        offs = torch.zeros(B + 1, dtype=torch.int64, pin_memory=True)
+        for _ in range(2):  # second call reuses the context's buffers
+            rc = lib.lrfb_qmf_encode_bytes_host(ctx, C.byref(cfg), B, C.c_void_p(imgs.data_ptr()), mj, len(mj),
+                                                C.c_void_p(blob.data_ptr()), cap, C.c_void_p(offs.data_ptr()))
+            _cabi.check(rc, "lrfb_qmf_encode_bytes_host")
+            o, b = offs.numpy(), blob.numpy()
+            assert [b[o[i]:o[i + 1]].tobytes() for i in range(B)] == want
+        rc = lib.lrfb_qmf_encode_bytes_host(ctx, C.byref(cfg), B, C.c_void_p(imgs.data_ptr()), mj, len(mj),
+                                            C.c_void_p(blob.data_ptr()), 1000, C.c_void_p(offs.data_ptr()))
+        assert rc == _cabi.LRFB_E_WORKSPACE if hasattr(_cabi, "LRFB_E_WORKSPACE") else rc != 0
+    finally:
+        lib.lrfb_ctx_destroy(ctx)
+    assert compression.qmf_encode_batch(imgs, quality=12) == want
