@@ -552,19 +552,27 @@ __global__ void __launch_bounds__(32, 16) deflate9_kernel(Params P) {
           const int chain = prev_length >= 32 ? 1024 : 4096;
           left = left < chain ? left : chain;
         }
-        // A candidate can only beat `best` if it agrees with the string at p on bytes 0..best.  Filter on eight of them:
-        // best-3..best (what zlib's own quick check looks at, twice as wide) and 3..6 (right after the hashed
-        // trigram, where most chain members of these smooth columns part ways): ~3 % of the candidates get through.
-        unsigned pe, pem, ps, psm;
+        // A candidate can only beat `best` if it agrees with the string at p on bytes 0..best.  Filter on four of them:
+        // best-1, best (zlib's own quick check) and 3, 4 (right after the hashed trigram, where most chain members of
+        // these smooth columns part ways): ~4.5 % of the candidates get through (12 % with zlib's two bytes alone).
+        unsigned ex = 0, exm = 0;
         auto set_filter = [&]() {
-          pe = ld4(data32, p + best - 3), pem = best == 2 ? 0xffffff00u : 0xffffffffu;
-          const int c = best - 2 < 4 ? best - 2 : 4;
-          ps = ld4(data32, p + 3), psm = c >= 4 ? 0xffffffffu : (1u << (8 * c)) - 1u;
+          ex = (unsigned)data[p + best] | ((unsigned)data[p + best - 1] << 8) | ((unsigned)data[p + 3] << 16) | ((unsigned)data[p + 4] << 24);
+          exm = 0xffffu | (best >= 3 ? 0xff0000u : 0u) | (best >= 4 ? 0xff000000u : 0u);
         };
         auto filter = [&](int q) {
-          return (((ld4(data32, q + best - 3) ^ pe) & pem) | ((ld4(data32, q + 3) ^ ps) & psm)) == 0u;
+          const unsigned char* dq = data + q;
+          const unsigned c = (unsigned)dq[best] | ((unsigned)dq[best - 1] << 8) | ((unsigned)dq[3] << 16) | ((unsigned)dq[4] << 24);
+          return ((c ^ ex) & exm) == 0u;
         };
-        if (left > 0) set_filter();
+        // the string at p, 4 bytes per lane (first 128 bytes), with the bytes beyond maxlen masked off
+        unsigned Pw = 0, lm = 0;
+        if (left > 0) {
+          set_filter();
+          const int nv = maxlen - 4 * lane;
+          lm = nv >= 4 ? 0xffffffffu : nv <= 0 ? 0u : (1u << (8 * nv)) - 1u;
+          if (lm) Pw = ld4(data32, p + 4 * lane);
+        }
         bool done = false;
         for (int k = (int)(rc & 0xffffu) - 1 - lane; left > 0 && !done; k -= 32 * kWide, left -= 32 * kWide) {
           // kWide x 32 candidates per step (order index j * 32 + lane): their loads overlap
@@ -581,18 +589,23 @@ __global__ void __launch_bounds__(32, 16) deflate9_kernel(Params P) {
               const int src = __ffs((int)mset) - 1;
               mset &= mset - 1;
               const int qq = __shfl_sync(0xffffffffu, q[j], src);
-              int len = maxlen;
-              for (int base = 0; base < maxlen; base += 128) {
-                const int off = base + 4 * lane, nv = maxlen - off;
-                unsigned x = 0;
-                if (nv > 0) {
-                  x = ld4(data32, p + off) ^ ld4(data32, qq + off);
-                  if (nv < 4) x &= (1u << (8 * nv)) - 1u;
-                }
-                const int mn = __reduce_min_sync(0xffffffffu, x ? off + ((__ffs((int)x) - 1) >> 3) : 0x7fff);
-                if (mn != 0x7fff) {
-                  len = mn;
-                  break;
+              unsigned x = 0;
+              if (lm) x = (Pw ^ ld4(data32, qq + 4 * lane)) & lm;
+              int len = __reduce_min_sync(0xffffffffu, x ? 4 * lane + ((__ffs((int)x) - 1) >> 3) : 0x7fff);
+              if (len == 0x7fff) {
+                len = maxlen;
+                for (int base = 128; base < maxlen; base += 128) {  // matches beyond 128 bytes: up to two more rounds
+                  const int off = base + 4 * lane, nv = maxlen - off;
+                  unsigned y = 0;
+                  if (nv > 0) {
+                    y = ld4(data32, p + off) ^ ld4(data32, qq + off);
+                    if (nv < 4) y &= (1u << (8 * nv)) - 1u;
+                  }
+                  const int mn = __reduce_min_sync(0xffffffffu, y ? off + ((__ffs((int)y) - 1) >> 3) : 0x7fff);
+                  if (mn != 0x7fff) {
+                    len = mn;
+                    break;
+                  }
                 }
               }
               if (len > best) {

@@ -1118,7 +1118,7 @@ struct lrfb_ctx {
   size_t blob_cap, offs_cap, pws_cap, hoffs_cap;
 #ifndef LRFB_SIM
   cudaStream_t back;     // D2H
-  cudaStream_t pack;     // lossless stage (overlaps the next chunk's encode kernels)
+  cudaStream_t pack[2];  // lossless stage, one stream per output slot: two chunks' deflate launches share the GPU with the next encode
   cudaEvent_t landed[kHostSlots], consumed[kHostSlots], encoded[2], drained[2], packed[2], sized[2];
 #endif
 };
@@ -1184,7 +1184,8 @@ LRFB_EXPORT int32_t lrfb_ctx_create(int32_t device, lrfb_ctx** out) {
   e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->back, cudaStreamNonBlocking);
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->pack, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->pack[0], cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->pack[1], cudaStreamNonBlocking);
   for (int i = 0; i < kHostSlots && e == cudaSuccess; ++i) {
     e = cudaEventCreateWithFlags(&c->landed[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->consumed[i], cudaEventDisableTiming);
@@ -1215,7 +1216,8 @@ LRFB_EXPORT void lrfb_ctx_destroy(lrfb_ctx* c) {
   for (int i = 0; i < kHostSlots; ++i) cudaEventDestroy(c->landed[i]), cudaEventDestroy(c->consumed[i]);
   for (int i = 0; i < 2; ++i)
     cudaEventDestroy(c->encoded[i]), cudaEventDestroy(c->drained[i]), cudaEventDestroy(c->packed[i]), cudaEventDestroy(c->sized[i]);
-  cudaStreamDestroy(c->pack);
+  cudaStreamDestroy(c->pack[0]);
+  cudaStreamDestroy(c->pack[1]);
   cudaStreamDestroy(c->back);
   cudaStreamDestroy(c->copy);
   cudaStreamDestroy(c->stream);
@@ -1615,7 +1617,8 @@ LRFB_EXPORT int32_t lrfb_qmf_encode_bytes_host(lrfb_ctx* c, const lrfb_qmf_confi
   if ((rc = grow(&c->d_ws, &c->ws_cap, (size_t)ws_need))) return rc;
   if ((rc = grow(&c->d_blob, &c->blob_cap, 2 * slot_blob))) return rc;
   if ((rc = grow(&c->d_offs, &c->offs_cap, 2 * slot_offs))) return rc;
-  if ((rc = grow(&c->d_pws, &c->pws_cap, (size_t)pws_need))) return rc;
+  const size_t slot_pws = ((size_t)pws_need + 255) & ~(size_t)255;
+  if ((rc = grow(&c->d_pws, &c->pws_cap, 2 * slot_pws))) return rc;
   if (c->hoffs_cap < 2 * slot_offs) {
 #ifndef LRFB_SIM
     if (c->h_offs) cudaFreeHost(c->h_offs);
@@ -1671,19 +1674,21 @@ LRFB_EXPORT int32_t lrfb_qmf_encode_bytes_host(lrfb_ctx* c, const lrfb_qmf_confi
       return rc;
     cudaEventRecord(c->consumed[slot], c->stream);
     cudaEventRecord(c->encoded[oslot], c->stream);
-    cudaStreamWaitEvent(c->pack, c->encoded[oslot], 0);
-    if (idx >= 2) cudaStreamWaitEvent(c->pack, c->drained[oslot], 0);  // blob of chunk idx-2 has left d_blob[oslot] (B(idx-2) ran)
-    if ((rc = lrfb_qmf_pack_device(cfg, n, d_out, metadata_json, metadata_len, d_blob, (int64_t)slot_blob, d_offs, c->d_pws,
-                                   (int64_t)c->pws_cap, (void*)(uintptr_t)c->pack)))
+    cudaStream_t ps = c->pack[oslot];
+    cudaStreamWaitEvent(ps, c->encoded[oslot], 0);
+    if (idx >= 2) cudaStreamWaitEvent(ps, c->drained[oslot], 0);  // blob of chunk idx-2 has left d_blob[oslot] (B(idx-2) ran)
+    if ((rc = lrfb_qmf_pack_device(cfg, n, d_out, metadata_json, metadata_len, d_blob, (int64_t)slot_blob, d_offs,
+                                   reinterpret_cast<unsigned char*>(c->d_pws) + (size_t)oslot * slot_pws, (int64_t)slot_pws,
+                                   (void*)(uintptr_t)ps)))
       return rc;
-    cudaEventRecord(c->packed[oslot], c->pack);
-    if ((rc = d2h(ho, d_offs, (size_t)(n + 1) * 8, c->pack))) return rc;
-    cudaEventRecord(c->sized[oslot], c->pack);
+    cudaEventRecord(c->packed[oslot], ps);
+    if ((rc = d2h(ho, d_offs, (size_t)(n + 1) * 8, ps))) return rc;
+    cudaEventRecord(c->sized[oslot], ps);
 #else
     if ((rc = h2d(d_in, src + (size_t)i0 * img_bytes, (size_t)n * img_bytes, c->stream))) return rc;
     if ((rc = lrfb_qmf_encode(cfg, n, d_in, d_out, c->d_ws, (int64_t)c->ws_cap, nullptr, nullptr))) return rc;
     if ((rc = lrfb_qmf_pack_device(cfg, n, d_out, metadata_json, metadata_len, d_blob, (int64_t)slot_blob, d_offs, c->d_pws,
-                                   (int64_t)c->pws_cap, nullptr)))
+                                   (int64_t)slot_pws, nullptr)))
       return rc;
     if ((rc = d2h(ho, d_offs, (size_t)(n + 1) * 8, c->stream))) return rc;
 #endif
@@ -1692,7 +1697,8 @@ LRFB_EXPORT int32_t lrfb_qmf_encode_bytes_host(lrfb_ctx* c, const lrfb_qmf_confi
   if ((rc = stage_b(n_chunks - 1))) return rc;
 #ifndef LRFB_SIM
   if ((rc = sync_stream(c->back))) return rc;
-  if ((rc = sync_stream(c->pack))) return rc;
+  if ((rc = sync_stream(c->pack[0]))) return rc;
+  if ((rc = sync_stream(c->pack[1]))) return rc;
 #endif
   return sync_stream(c->stream);
 }

@@ -59,14 +59,14 @@ def _records(rng, lay, count):
     return recs
 
 
-@pytest.mark.parametrize("shape,quality", [((48, 64), 7), ((96, 160), 25)])
-def test_kernel_on_shim_matches_python_packer(shape, quality):
+@pytest.mark.parametrize("shape,quality,count", [((48, 64), 7, 4), ((96, 160), 25, 3)])
+def test_kernel_on_shim_matches_python_packer(shape, quality, count):
     from cpu_sim import simlib
 
     H, W = shape
     cfg, lay = compression.resolve_plan(H, W, None, quality, "YCbCr", (0.5, 0.5), (8, 8), (-16, 15), 10)
     meta = compression._metadata(torch.uint8, "YCbCr", True, (-16, 15), (8, 8), lay)
-    recs = _records(np.random.default_rng(5), lay, 5)
+    recs = _records(np.random.default_rng(5), lay, count)
     want = [packing.pack_qmf_record(recs[i], lay, meta) for i in range(len(recs))]
     got = simlib.pack_device(recs, cfg, packing.dict_to_bytes(meta))
     assert got == want
