@@ -376,17 +376,110 @@ struct Params {
 __host__ __device__ inline int pad_len(int len) { return (len + 63) & ~63; }
 __host__ __device__ inline long long scratch_per_cta(int len) { return 7ll * pad_len(len); }
 __host__ __device__ inline int smem_data(int len) { return (len + 16 + 15) & ~15; }
-constexpr int kFreqPad = (kFreqBytes + 15) & ~15, kCntBytes = 2 * (256 + 128), kTreePad = (kTreeBytes + 15) & ~15;
+constexpr int kFreqPad = (kFreqBytes + 15) & ~15, kCntBytes = 2 * (256 + 128), kTaskBytes = 64, kTreePad = (kTreeBytes + 15) & ~15;
 __host__ __device__ inline int smem_region(int len) {
   const int a = 2 * pad_len(len), b = kTreePad + ((len + 32 + 15) & ~15);
   return a > b ? a : b;
 }
-__host__ __device__ inline int smem_bytes(int len) { return smem_data(len) + kFreqPad + kCntBytes + smem_region(len); }
+__host__ __device__ inline int smem_bytes(int len) { return smem_data(len) + kFreqPad + kCntBytes + kTaskBytes + smem_region(len); }
 
-constexpr int kWide = 4;  // chain candidates per lane and step
+constexpr int kWarps = 4;             // warps per column: warp 0 runs the serial parts, every warp walks its share of long chains
+constexpr int kWide = 2;              // chain candidates per lane and step
+constexpr int kStep = 32 * kWide;     // candidates per step of one warp
+constexpr int kParMin = 4 * kStep;    // chains with more candidates than this are walked by all warps of the CTA
+struct Task {
+  int p, best, maxlen, rank, left, cmd;  // cmd 1: walk, 2: the parse of this column is over
+  unsigned key;                           // result: (length << 12) | (4095 - chain index), atomicMax over the warps
+  int nice_idx;                           // smallest chain index that reached nice_length so far (walks stop beyond it)
+  int stream;
+};
 __device__ __forceinline__ unsigned ld4(const unsigned* w, int off) {
   const int i = off >> 2;
   return __funnelshift_r(w[i], w[i + 1], (off & 3) * 8);
+}
+// Walk the chain candidates with index s0 = w*kStep, (w+nw)*kStep, ... < left (index 0 = newest = A[rank-1]) and return the
+// longest match beyond `best` and the chain index of the closest candidate that has it.  A candidate can only beat
+// `best` if it agrees with the string at p on bytes 0..best; filter on four of them: best-1, best (zlib's own quick
+// check) and 3, 4 (right after the hashed trigram, where most chain members of these smooth columns part ways): ~4.5 %
+// get through (12 % with zlib's two bytes alone).  Survivors are compared by the whole warp, 128 bytes per round, in chain
+// order, so `best` tightens exactly as in the serial walk; the first candidate that reaches maxlen (nice_length or the
+// end of the input) ends the walk — zlib stops there too — and candidates beyond it never matter because no length exceeds it.
+__device__ __forceinline__ void walk_chain(const unsigned char* data, const unsigned* data32, const unsigned short* A,
+                                           int p, int rank, int left, int maxlen, int w, int nw, int* nice_idx, int lane,
+                                           int& best, int& bidx) {
+  unsigned ex = 0, exm = 0;
+  auto set_filter = [&]() {
+    ex = (unsigned)data[p + best] | ((unsigned)data[p + best - 1] << 8) | ((unsigned)data[p + 3] << 16) | ((unsigned)data[p + 4] << 24);
+    exm = 0xffffu | (best >= 3 ? 0xff0000u : 0u) | (best >= 4 ? 0xff000000u : 0u);
+  };
+  auto filter = [&](int q) {
+    const unsigned char* dq = data + q;
+    const unsigned c = (unsigned)dq[best] | ((unsigned)dq[best - 1] << 8) | ((unsigned)dq[3] << 16) | ((unsigned)dq[4] << 24);
+    return ((c ^ ex) & exm) == 0u;
+  };
+  if (w * kStep >= left) return;
+  set_filter();
+  // the string at p, 4 bytes per lane (first 128 bytes), with the bytes beyond maxlen masked off
+  const int nv0 = maxlen - 4 * lane;
+  const unsigned lm = nv0 >= 4 ? 0xffffffffu : nv0 <= 0 ? 0u : (1u << (8 * nv0)) - 1u;
+  const unsigned Pw = lm ? ld4(data32, p + 4 * lane) : 0u;
+  for (int s0 = w * kStep; s0 < left; s0 += nw * kStep) {
+    if (nice_idx && s0 > *reinterpret_cast<volatile int*>(nice_idx)) break;  // a closer candidate already ended the walk
+    int q[kWide];
+    unsigned pm[kWide];
+#pragma unroll
+    for (int j = 0; j < kWide; ++j) {
+      const int idx = s0 + 32 * j + lane;
+      q[j] = idx < left ? A[rank - 1 - idx] : 0;
+    }
+#pragma unroll
+    for (int j = 0; j < kWide; ++j) pm[j] = __ballot_sync(0xffffffffu, q[j] != 0 && filter(q[j]));
+    bool done = false;
+#pragma unroll
+    for (int j = 0; j < kWide; ++j) {
+      unsigned mset = pm[j];
+      while (mset) {
+        const int src = __ffs((int)mset) - 1;
+        mset &= mset - 1;
+        const int qq = __shfl_sync(0xffffffffu, q[j], src);
+        unsigned x = 0;
+        if (lm) x = (Pw ^ ld4(data32, qq + 4 * lane)) & lm;
+        int len = __reduce_min_sync(0xffffffffu, x ? 4 * lane + ((__ffs((int)x) - 1) >> 3) : 0x7fff);
+        if (len == 0x7fff) {
+          len = maxlen;
+          for (int base = 128; base < maxlen; base += 128) {  // matches beyond 128 bytes: up to two more rounds
+            const int off = base + 4 * lane, nv = maxlen - off;
+            unsigned y = 0;
+            if (nv > 0) {
+              y = ld4(data32, p + off) ^ ld4(data32, qq + off);
+              if (nv < 4) y &= (1u << (8 * nv)) - 1u;
+            }
+            const int mn = __reduce_min_sync(0xffffffffu, y ? off + ((__ffs((int)y) - 1) >> 3) : 0x7fff);
+            if (mn != 0x7fff) {
+              len = mn;
+              break;
+            }
+          }
+        }
+        if (len > best) {
+          best = len, bidx = s0 + 32 * j + src;
+          if (best >= maxlen) {
+            done = true;
+            break;
+          }
+          set_filter();  // the rest of this step is re-filtered against the new best
+          mset = __ballot_sync(0xffffffffu, lane > src && q[j] != 0 && filter(q[j]));
+#pragma unroll
+          for (int j2 = j + 1; j2 < kWide; ++j2) pm[j2] = __ballot_sync(0xffffffffu, q[j2] != 0 && filter(q[j2]));
+        }
+      }
+      if (done) break;
+    }
+    if (done) {
+      if (nice_idx && lane == 0) atomicMin(nice_idx, bidx);
+      break;
+    }
+  }
 }
 __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 #pragma unroll
@@ -397,15 +490,24 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
   return v;
 }
 
-__global__ void __launch_bounds__(32, 16) deflate9_kernel(Params P) {
+#ifdef D9_PROF
+__device__ unsigned long long g_d9_prof[16];
+#define D9_T(i) do { if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&g_d9_prof[i], (unsigned long long)(t_ - t_prof)); t_prof = t_; } } while (0)
+#define D9_C(i, v) do { if (threadIdx.x == 0) atomicAdd(&g_d9_prof[i], (unsigned long long)(v)); } while (0)
+#else
+#define D9_T(i)
+#define D9_C(i, v)
+#endif
+__global__ void __launch_bounds__(32 * kWarps, 8) deflate9_kernel(Params P) {
   LRFB_DYN_SMEM(smem);
-  const int lane = threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = P.len, m = n >= 3 ? n - 2 : 0, lp = pad_len(n);
   unsigned char* data = smem;
   const unsigned* data32 = reinterpret_cast<const unsigned*>(smem);
   unsigned char* freq_mem = smem + smem_data(n);
   unsigned short* cnt = reinterpret_cast<unsigned short*>(freq_mem + kFreqPad);  // [256] low digit, [128] high digit
-  unsigned char* region = freq_mem + kFreqPad + kCntBytes;
+  Task* task = reinterpret_cast<Task*>(freq_mem + kFreqPad + kCntBytes);
+  unsigned char* region = freq_mem + kFreqPad + kCntBytes + kTaskBytes;
   unsigned short* A = reinterpret_cast<unsigned short*>(region);  // positions sorted by (hash, position)
   unsigned char* scr = P.scratch + (long long)blockIdx.x * scratch_per_cta(n);
   unsigned short* B = reinterpret_cast<unsigned short*>(scr);                // sort ping-pong, dead once RC is written
@@ -415,10 +517,23 @@ __global__ void __launch_bounds__(32, 16) deflate9_kernel(Params P) {
   const int n_streams = P.batch * P.cols_per_image;
 
   for (;;) {
-    int s = 0;
-    if (lane == 0) s = atomicAdd(P.counter, 1);
-    s = __shfl_sync(0xffffffffu, s, 0);
+    if (threadIdx.x == 0) task->stream = atomicAdd(P.counter, 1);
+    __syncthreads();
+    const int s = task->stream;
     if (s >= n_streams) break;
+    if (warp != 0) {
+      // helper warps: wait for the long chain walks warp 0 publishes, take every kWarps-th step of them
+      for (;;) {
+        __syncthreads();
+        if (*reinterpret_cast<volatile int*>(&task->cmd) == 2) break;
+        const int tp = task->p, tmax = task->maxlen, trank = task->rank, tleft = task->left;
+        int best = task->best, bidx = -1;
+        walk_chain(data, data32, A, tp, trank, tleft, tmax, warp, kWarps, &task->nice_idx, lane, best, bidx);
+        if (bidx >= 0 && lane == 0) atomicMax(&task->key, ((unsigned)best << 12) | (unsigned)(4095 - bidx));
+        __syncthreads();
+      }
+      continue;
+    }
     const int img = s / P.cols_per_image;
     int j = s - img * P.cols_per_image, sg = 0;
     while (sg + 1 < P.n_seg && j >= P.seg[sg].ncols) j -= P.seg[sg].ncols, ++sg;
@@ -426,6 +541,9 @@ __global__ void __launch_bounds__(32, 16) deflate9_kernel(Params P) {
     unsigned char* dst = P.cbuf + (long long)img * P.img_stride + P.seg[sg].out_off + (long long)j * P.slot;
     unsigned* dsize = P.csize + (long long)img * P.cols_total + P.seg[sg].col0 + j;
 
+#ifdef D9_PROF
+    long long t_prof = clock64();
+#endif
     // ---- load the column, clear the counters --------------------------------------------------------------------
     if ((((unsigned long long)src) & 15) == 0 && (n & 15) == 0) {
       for (int i = lane * 16; i < n; i += 512) *reinterpret_cast<uint4*>(data + i) = *reinterpret_cast<const uint4*>(src + i);
@@ -433,7 +551,7 @@ __global__ void __launch_bounds__(32, 16) deflate9_kernel(Params P) {
       for (int i = lane; i < n; i += 32) data[i] = src[i];
     }
     for (int i = n + lane; i < smem_data(n); i += 32) data[i] = 0;
-    for (int i = lane; i < (kFreqPad + kCntBytes) / 4; i += 32) reinterpret_cast<unsigned*>(freq_mem)[i] = 0;
+    for (int i = lane; i < (kFreqPad + kCntBytes) / 4; i += 32) reinterpret_cast<unsigned*>(freq_mem)[i] = 0;  // not the task
     __syncwarp();
 
     // ---- positions sorted by (hash, position): two stable counting passes (8 + 7 bits) ----------------------------
@@ -493,6 +611,7 @@ __global__ void __launch_bounds__(32, 16) deflate9_kernel(Params P) {
         __syncwarp();
       }
     }
+    D9_T(0);  // load + sort
     {  // per position: its rank in A and the number of chain candidates below it (same hash, position 0 excluded: NIL)
       int run_start = 0, kzero = -1, carry_h = -1;
       for (int base = 0; base < m; base += 32) {
@@ -522,109 +641,65 @@ __global__ void __launch_bounds__(32, 16) deflate9_kernel(Params P) {
     }
     __syncwarp();
 
+    D9_T(1);  // ranks
     // ---- deflate_slow ------------------------------------------------------------------------------------------------
     unsigned short* lfreq = reinterpret_cast<unsigned short*>(freq_mem);
     unsigned short* dfreq = lfreq + kHeap;
     int strstart = 0, lookahead = n, match_length = 2, match_start = 0, match_available = 0, ns = 0;
+    // rank | candidates of 128 positions ahead of the parse live in four registers per lane; the far half is
+    // requested from L2 64 positions before it is needed
     int wbase = -1000000;
-    unsigned rk_cur = 0, rk_nxt = 0;
+    unsigned w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+    auto ldrc = [&](int i) { return i < m ? __ldcg(RC + i) : 0u; };
     while (lookahead > 0) {
       const int prev_length = match_length, prev_match = match_start;
       match_length = 2;
       const int maxlen = lookahead < 258 ? lookahead : 258;
       if (lookahead >= 3 && prev_length < maxlen) {
         const int p = strstart;
-        if (p < wbase || p - wbase >= 64) {
+        if (p < wbase || p - wbase >= 128) {
           wbase = p & ~31;
-          rk_cur = (wbase + lane < m) ? __ldcg(RC + wbase + lane) : 0u;
-          rk_nxt = (wbase + 32 + lane < m) ? __ldcg(RC + wbase + 32 + lane) : 0u;
-        } else if (p - wbase >= 32) {
-          wbase += 32;
-          rk_cur = rk_nxt;
-          rk_nxt = (wbase + 32 + lane < m) ? __ldcg(RC + wbase + 32 + lane) : 0u;
+          w0 = ldrc(wbase + lane), w1 = ldrc(wbase + 32 + lane), w2 = ldrc(wbase + 64 + lane), w3 = ldrc(wbase + 96 + lane);
+        } else if (p - wbase >= 64) {
+          wbase += 64;
+          w0 = w2, w1 = w3;
+          w2 = ldrc(wbase + 64 + lane), w3 = ldrc(wbase + 96 + lane);
         }
-        const unsigned rc = __shfl_sync(0xffffffffu, rk_cur, p - wbase);
-        int best = prev_length, bpos = match_start;
+        const int wi = (p - wbase) >> 5;
+        const unsigned rc = __shfl_sync(0xffffffffu, wi == 0 ? w0 : wi == 1 ? w1 : wi == 2 ? w2 : w3, (p - wbase) & 31);
         // zlib walks at most max_chain (4096; a quarter once the previous match is >= good_length) candidates, newest
-        // first; here they are A[r-1], A[r-2], ... and 32 of them are tested per step
+        // first; here they are A[rank-1], A[rank-2], ...
+        const int rank = (int)(rc & 0xffffu);
         int left = (int)(rc >> 16);
         {
           const int chain = prev_length >= 32 ? 1024 : 4096;
           left = left < chain ? left : chain;
         }
-        // A candidate can only beat `best` if it agrees with the string at p on bytes 0..best.  Filter on four of them:
-        // best-1, best (zlib's own quick check) and 3, 4 (right after the hashed trigram, where most chain members of
-        // these smooth columns part ways): ~4.5 % of the candidates get through (12 % with zlib's two bytes alone).
-        unsigned ex = 0, exm = 0;
-        auto set_filter = [&]() {
-          ex = (unsigned)data[p + best] | ((unsigned)data[p + best - 1] << 8) | ((unsigned)data[p + 3] << 16) | ((unsigned)data[p + 4] << 24);
-          exm = 0xffffu | (best >= 3 ? 0xff0000u : 0u) | (best >= 4 ? 0xff000000u : 0u);
-        };
-        auto filter = [&](int q) {
-          const unsigned char* dq = data + q;
-          const unsigned c = (unsigned)dq[best] | ((unsigned)dq[best - 1] << 8) | ((unsigned)dq[3] << 16) | ((unsigned)dq[4] << 24);
-          return ((c ^ ex) & exm) == 0u;
-        };
-        // the string at p, 4 bytes per lane (first 128 bytes), with the bytes beyond maxlen masked off
-        unsigned Pw = 0, lm = 0;
-        if (left > 0) {
-          set_filter();
-          const int nv = maxlen - 4 * lane;
-          lm = nv >= 4 ? 0xffffffffu : nv <= 0 ? 0u : (1u << (8 * nv)) - 1u;
-          if (lm) Pw = ld4(data32, p + 4 * lane);
-        }
-        bool done = false;
-        for (int k = (int)(rc & 0xffffu) - 1 - lane; left > 0 && !done; k -= 32 * kWide, left -= 32 * kWide) {
-          // kWide x 32 candidates per step (order index j * 32 + lane): their loads overlap
-          int q[kWide];
-          unsigned pm[kWide];
-#pragma unroll
-          for (int j = 0; j < kWide; ++j) q[j] = (32 * j + lane < left) ? A[k - 32 * j] : 0;
-#pragma unroll
-          for (int j = 0; j < kWide; ++j) pm[j] = __ballot_sync(0xffffffffu, q[j] != 0 && filter(q[j]));
-#pragma unroll
-          for (int j = 0; j < kWide; ++j) {
-            unsigned mset = pm[j];
-            while (mset) {  // the survivors in chain order, each compared by the whole warp (128 bytes per round)
-              const int src = __ffs((int)mset) - 1;
-              mset &= mset - 1;
-              const int qq = __shfl_sync(0xffffffffu, q[j], src);
-              unsigned x = 0;
-              if (lm) x = (Pw ^ ld4(data32, qq + 4 * lane)) & lm;
-              int len = __reduce_min_sync(0xffffffffu, x ? 4 * lane + ((__ffs((int)x) - 1) >> 3) : 0x7fff);
-              if (len == 0x7fff) {
-                len = maxlen;
-                for (int base = 128; base < maxlen; base += 128) {  // matches beyond 128 bytes: up to two more rounds
-                  const int off = base + 4 * lane, nv = maxlen - off;
-                  unsigned y = 0;
-                  if (nv > 0) {
-                    y = ld4(data32, p + off) ^ ld4(data32, qq + off);
-                    if (nv < 4) y &= (1u << (8 * nv)) - 1u;
-                  }
-                  const int mn = __reduce_min_sync(0xffffffffu, y ? off + ((__ffs((int)y) - 1) >> 3) : 0x7fff);
-                  if (mn != 0x7fff) {
-                    len = mn;
-                    break;
-                  }
-                }
-              }
-              if (len > best) {
-                best = len, bpos = qq;
-                if (best >= maxlen) {  // nice_length (or the end of the input): zlib stops at the first such candidate
-                  done = true;
-                  break;
-                }
-                set_filter();  // the rest of this step is re-filtered against the new best
-                mset = __ballot_sync(0xffffffffu, lane > src && q[j] != 0 && filter(q[j]));
-#pragma unroll
-                for (int j2 = j + 1; j2 < kWide; ++j2) pm[j2] = __ballot_sync(0xffffffffu, q[j2] != 0 && filter(q[j2]));
-              }
-            }
-            if (done) break;
+        int best = prev_length, bidx = -1;
+        D9_T(2);  // parse control
+        if (left > kParMin) {  // long chain: every warp of the CTA takes every kWarps-th step; longest-then-closest by atomicMax
+          if (lane == 0) {
+            task->p = p, task->best = best, task->maxlen = maxlen, task->rank = rank, task->left = left, task->cmd = 1;
+            task->key = 0, task->nice_idx = 0x7fffffff;
           }
+          __syncthreads();
+          walk_chain(data, data32, A, p, rank, left, maxlen, 0, kWarps, &task->nice_idx, lane, best, bidx);
+          if (bidx >= 0 && lane == 0) atomicMax(&task->key, ((unsigned)best << 12) | (unsigned)(4095 - bidx));
+          __syncthreads();
+          const unsigned key = *reinterpret_cast<volatile unsigned*>(&task->key);
+          bidx = -1;
+          if (key) best = (int)(key >> 12), bidx = 4095 - (int)(key & 4095u);
+          D9_T(3);  // long walks
+          D9_C(8, 1);
+          D9_C(9, left);
+        } else {
+          walk_chain(data, data32, A, p, rank, left, maxlen, 0, 1, nullptr, lane, best, bidx);
+          D9_T(4);  // short walks
+          D9_C(10, 1);
+          D9_C(11, left);
         }
         match_length = best;
-        match_start = bpos;
+        if (bidx >= 0) match_start = A[rank - 1 - bidx];
         if (match_length == 3 && p - match_start > 4096) match_length = 2;
       }
       if (prev_length >= 3 && match_length <= prev_length) {
@@ -655,7 +730,9 @@ __global__ void __launch_bounds__(32, 16) deflate9_kernel(Params P) {
       }
       ++ns;
     }
-    __syncwarp();
+    D9_T(2);
+    if (lane == 0) task->cmd = 2;
+    __syncthreads();  // the helper warps leave; A may now be overwritten
 
     // ---- trees and block header (lane 0), then the symbols on all lanes ----------------------------------------------
     unsigned* words = reinterpret_cast<unsigned*>(region + kTreePad);
@@ -675,6 +752,7 @@ __global__ void __launch_bounds__(32, 16) deflate9_kernel(Params P) {
     type = __shfl_sync(0xffffffffu, type, 0);
     bitpos = __shfl_sync(0xffffffffu, bitpos, 0);
     __syncwarp();
+    D9_T(5);  // trees + header
     unsigned long long sa = 0, sb = 0;  // adler32: a = 1 + sum d_i, b = n + sum (n - i) d_i
     for (int i = lane; i < n; i += 32) sa += data[i], sb += (unsigned long long)(n - i) * data[i];
 #pragma unroll
@@ -719,6 +797,7 @@ __global__ void __launch_bounds__(32, 16) deflate9_kernel(Params P) {
       __syncwarp();
       for (int i = lane; i < (total + 3) / 4; i += 32) reinterpret_cast<unsigned*>(dst)[i] = words[i];
     }
+    D9_T(6);  // symbols + copy out
     if (lane == 0) *dsize = (unsigned)total;
     __syncwarp();
   }

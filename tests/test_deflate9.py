@@ -122,7 +122,7 @@ def test_encode_bytes_host_pipeline_ragged_chunks():
     ctx = C.c_void_p()
     _cabi.check(lib.lrfb_ctx_create(0, C.byref(ctx)), "ctx")
     try:
-        _cabi.check(lib.lrfb_ctx_set_chunk_bytes(ctx, 8 * 3 * H * W), "chunk")  # 8 images per chunk: 4 full + 5
+        _cabi.check(lib.lrfb_ctx_set_chunk_bytes(ctx, 2 * 3 * H * W), "chunk")  # 4 x 2 = 8 images per chunk: 4 full + 5
         mj = packing.dict_to_bytes(meta)
         cap = B * int(lib.lrfb_qmf_pack_bound(C.byref(cfg), len(mj)))
         blob = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
