@@ -383,6 +383,14 @@ __host__ __device__ inline int smem_region(int len) {
 }
 __host__ __device__ inline int smem_bytes(int len) { return smem_data(len) + kFreqPad + kCntBytes + kTaskBytes + smem_region(len); }
 
+#ifdef D9_PROF
+__device__ unsigned long long g_d9_prof[16];
+#define D9_T(i) do { if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&g_d9_prof[i], (unsigned long long)(t_ - t_prof)); t_prof = t_; } } while (0)
+#define D9_C(i, v) do { if (threadIdx.x == 0) atomicAdd(&g_d9_prof[i], (unsigned long long)(v)); } while (0)
+#else
+#define D9_T(i)
+#define D9_C(i, v)
+#endif
 constexpr int kWarps = 4;             // warps per column: warp 0 runs the serial parts, every warp walks its share of long chains
 constexpr int kWide = 2;              // chain candidates per lane and step
 constexpr int kStep = 32 * kWide;     // candidates per step of one warp
@@ -407,24 +415,30 @@ __device__ __forceinline__ unsigned ld4(const unsigned* w, int off) {
 __device__ __forceinline__ void walk_chain(const unsigned char* data, const unsigned* data32, const unsigned short* A,
                                            int p, int rank, int left, int maxlen, int w, int nw, int* nice_idx, int lane,
                                            int& best, int& bidx) {
+  // filter offsets f1, f2 start at 3, 4 and then follow the survivors: where the last ones parted from the string at p
+  // the next chain members usually do too (1 % get through instead of 2.7 %)
   unsigned ex = 0, exm = 0;
+  int f1 = 3, f2 = 4;
   auto set_filter = [&]() {
-    ex = (unsigned)data[p + best] | ((unsigned)data[p + best - 1] << 8) | ((unsigned)data[p + 3] << 16) | ((unsigned)data[p + 4] << 24);
-    exm = 0xffffu | (best >= 3 ? 0xff0000u : 0u) | (best >= 4 ? 0xff000000u : 0u);
+    ex = (unsigned)data[p + best] | ((unsigned)data[p + best - 1] << 8) | ((unsigned)data[p + f1] << 16) | ((unsigned)data[p + f2] << 24);
+    exm = 0xffffu | (best >= f1 ? 0xff0000u : 0u) | (best >= f2 ? 0xff000000u : 0u);
   };
   auto filter = [&](int q) {
     const unsigned char* dq = data + q;
-    const unsigned c = (unsigned)dq[best] | ((unsigned)dq[best - 1] << 8) | ((unsigned)dq[3] << 16) | ((unsigned)dq[4] << 24);
+    const unsigned c = (unsigned)dq[best] | ((unsigned)dq[best - 1] << 8) | ((unsigned)dq[f1] << 16) | ((unsigned)dq[f2] << 24);
     return ((c ^ ex) & exm) == 0u;
   };
   if (w * kStep >= left) return;
   set_filter();
+  bool dirty = false;
   // the string at p, 4 bytes per lane (first 128 bytes), with the bytes beyond maxlen masked off
   const int nv0 = maxlen - 4 * lane;
   const unsigned lm = nv0 >= 4 ? 0xffffffffu : nv0 <= 0 ? 0u : (1u << (8 * nv0)) - 1u;
   const unsigned Pw = lm ? ld4(data32, p + 4 * lane) : 0u;
   for (int s0 = w * kStep; s0 < left; s0 += nw * kStep) {
     if (nice_idx && s0 > *reinterpret_cast<volatile int*>(nice_idx)) break;  // a closer candidate already ended the walk
+    if (dirty) set_filter(), dirty = false;
+    D9_C(12, 1);
     int q[kWide];
     unsigned pm[kWide];
 #pragma unroll
@@ -442,6 +456,7 @@ __device__ __forceinline__ void walk_chain(const unsigned char* data, const unsi
         const int src = __ffs((int)mset) - 1;
         mset &= mset - 1;
         const int qq = __shfl_sync(0xffffffffu, q[j], src);
+        D9_C(13, 1);
         unsigned x = 0;
         if (lm) x = (Pw ^ ld4(data32, qq + 4 * lane)) & lm;
         int len = __reduce_min_sync(0xffffffffu, x ? 4 * lane + ((__ffs((int)x) - 1) >> 3) : 0x7fff);
@@ -463,11 +478,20 @@ __device__ __forceinline__ void walk_chain(const unsigned char* data, const unsi
         }
         if (len > best) {
           best = len, bidx = s0 + 32 * j + src;
+          D9_C(14, 1);
           if (best >= maxlen) {
             done = true;
             break;
           }
-          set_filter();  // the rest of this step is re-filtered against the new best
+        } else {
+          f2 = f1, f1 = len;  // this survivor parted from the string at offset len <= best
+        }
+        dirty = true;
+        bool more = mset != 0;
+#pragma unroll
+        for (int j2 = j + 1; j2 < kWide; ++j2) more |= pm[j2] != 0;
+        if (more) {  // the rest of this step is re-filtered against the new best / the new offsets
+          set_filter(), dirty = false;
           mset = __ballot_sync(0xffffffffu, lane > src && q[j] != 0 && filter(q[j]));
 #pragma unroll
           for (int j2 = j + 1; j2 < kWide; ++j2) pm[j2] = __ballot_sync(0xffffffffu, q[j2] != 0 && filter(q[j2]));
@@ -490,14 +514,6 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
   return v;
 }
 
-#ifdef D9_PROF
-__device__ unsigned long long g_d9_prof[16];
-#define D9_T(i) do { if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&g_d9_prof[i], (unsigned long long)(t_ - t_prof)); t_prof = t_; } } while (0)
-#define D9_C(i, v) do { if (threadIdx.x == 0) atomicAdd(&g_d9_prof[i], (unsigned long long)(v)); } while (0)
-#else
-#define D9_T(i)
-#define D9_C(i, v)
-#endif
 __global__ void __launch_bounds__(32 * kWarps, 8) deflate9_kernel(Params P) {
   LRFB_DYN_SMEM(smem);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

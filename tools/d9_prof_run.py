@@ -29,4 +29,5 @@ v = list(out)
 names = ["load+sort", "ranks", "parse ctl", "long walks", "short walks", "trees+hdr", "symbols+out"]
 tot = sum(v[:7])
 for n_, x in zip(names, v[:7]): print(f"{n_:12s} {x/1e6:10.1f} Mcycles {100*x/tot:5.1f}%")
+print("master steps", v[12], "survivors", v[13], "improvements", v[14])
 print("long searches", v[8], "candidates", v[9], "| short searches", v[10], "candidates", v[11])
