@@ -468,7 +468,7 @@ def main():
     # ---- end to end to `bytes` through the Python API: pinned host uint8 images -> list[bytes] -------------------------
     if not args.quick:
         n_b = min(B, args.bytes_images)
-        lrf_b200.qmf_encode_batch(h_in[:64], **KW)
+        lrf_b200.qmf_encode_batch(h_in[:n_b], **KW)  # warm-up at the same size: the context's buffers are grow-only
         barrier()
         t0 = time.perf_counter()
         out_b = lrf_b200.qmf_encode_batch(h_in[:n_b], **KW)

@@ -294,7 +294,7 @@ __host__ __device__ inline void send_tree(const Tree& t, const Work& w, int max_
 // counts (END_BLOCK included), internal nodes and b.freq are cleared here.  Returns the block type (0 stored, 1 static,
 // 2 dynamic); for 1 and 2 the 3 header bits (+ the tree header) are written at o and l/d code + len describe the
 // code to use for every symbol.
-__host__ __device__ inline int begin_block(Work& w, int stored_len, BitW& o) {
+__host__ __device__ inline int begin_block(Work& w, int stored_len, BitW& o, bool fill_static = true) {
   w.opt_len = 0, w.static_len = 0;
   for (int i = 0; i < kBLCodes; ++i) w.b.freq[i] = 0;
   build_tree(w.l, w);
@@ -312,6 +312,7 @@ __host__ __device__ inline int begin_block(Work& w, int stored_len, BitW& o) {
   if ((unsigned)stored_len + 4 <= opt_lenb) return 0;
   if (static_lenb == opt_lenb) {
     o.put((1 << 1) + 1, 3);
+    if (!fill_static) return 1;  // the caller writes the fixed code (the kernel does it on all lanes)
     for (int n = 0; n < kLCodes; ++n) w.l.code[n] = (unsigned short)bi_reverse(static_lcode(n), static_llen(n)), w.l.len[n] = (unsigned char)static_llen(n);
     for (int n = 0; n < kDCodes; ++n) w.d.code[n] = (unsigned short)bi_reverse((unsigned)n, 5), w.d.len[n] = 5;
     return 1;
@@ -391,7 +392,11 @@ __device__ unsigned long long g_d9_prof[16];
 #define D9_T(i)
 #define D9_C(i, v)
 #endif
-constexpr int kWarps = 4;             // warps per column: warp 0 runs the serial parts, every warp walks its share of long chains
+constexpr int kWarps = 4;             // warps per long column: warp 0 runs the serial parts, every warp walks its share of long chains
+#ifndef D9_LONG
+#define D9_LONG 2048
+#endif
+constexpr int kLongColumn = D9_LONG;     // columns above this many bytes get kWarps warps, the others one
 constexpr int kWide = 2;              // chain candidates per lane and step
 constexpr int kStep = 32 * kWide;     // candidates per step of one warp
 constexpr int kParMin = 4 * kStep;    // chains with more candidates than this are walked by all warps of the CTA
@@ -514,7 +519,8 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
   return v;
 }
 
-__global__ void __launch_bounds__(32 * kWarps, 8) deflate9_kernel(Params P) {
+template <int NW>  // warps per column: 4 for long columns (shared chain walks), 1 for short ones (more columns per SM)
+__global__ void __launch_bounds__(32 * NW, NW == 1 ? 32 : 8) deflate9_kernel(Params P) {
   LRFB_DYN_SMEM(smem);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = P.len, m = n >= 3 ? n - 2 : 0, lp = pad_len(n);
@@ -544,7 +550,7 @@ __global__ void __launch_bounds__(32 * kWarps, 8) deflate9_kernel(Params P) {
         if (*reinterpret_cast<volatile int*>(&task->cmd) == 2) break;
         const int tp = task->p, tmax = task->maxlen, trank = task->rank, tleft = task->left;
         int best = task->best, bidx = -1;
-        walk_chain(data, data32, A, tp, trank, tleft, tmax, warp, kWarps, &task->nice_idx, lane, best, bidx);
+        walk_chain(data, data32, A, tp, trank, tleft, tmax, warp, NW, &task->nice_idx, lane, best, bidx);
         if (bidx >= 0 && lane == 0) atomicMax(&task->key, ((unsigned)best << 12) | (unsigned)(4095 - bidx));
         __syncthreads();
       }
@@ -693,13 +699,13 @@ __global__ void __launch_bounds__(32 * kWarps, 8) deflate9_kernel(Params P) {
         }
         int best = prev_length, bidx = -1;
         D9_T(2);  // parse control
-        if (left > kParMin) {  // long chain: every warp of the CTA takes every kWarps-th step; longest-then-closest by atomicMax
+        if (NW > 1 && left > kParMin) {  // long chain: every warp of the CTA takes every NW-th step; longest-then-closest by atomicMax
           if (lane == 0) {
             task->p = p, task->best = best, task->maxlen = maxlen, task->rank = rank, task->left = left, task->cmd = 1;
             task->key = 0, task->nice_idx = 0x7fffffff;
           }
           __syncthreads();
-          walk_chain(data, data32, A, p, rank, left, maxlen, 0, kWarps, &task->nice_idx, lane, best, bidx);
+          walk_chain(data, data32, A, p, rank, left, maxlen, 0, NW, &task->nice_idx, lane, best, bidx);
           if (bidx >= 0 && lane == 0) atomicMax(&task->key, ((unsigned)best << 12) | (unsigned)(4095 - bidx));
           __syncthreads();
           const unsigned key = *reinterpret_cast<volatile unsigned*>(&task->key);
@@ -762,11 +768,15 @@ __global__ void __launch_bounds__(32 * kWarps, 8) deflate9_kernel(Params P) {
       lfreq[256] = 1;
       words[0] = 0xDA78u;
       BitW o{words, 16};
-      type = begin_block(w, n, o);
+      type = begin_block(w, n, o, false);
       bitpos = o.pos;
     }
     type = __shfl_sync(0xffffffffu, type, 0);
     bitpos = __shfl_sync(0xffffffffu, bitpos, 0);
+    if (type == 1) {  // fixed Huffman code
+      for (int c = lane; c < kLCodes; c += 32) w.l.code[c] = (unsigned short)bi_reverse(static_lcode(c), static_llen(c)), w.l.len[c] = (unsigned char)static_llen(c);
+      if (lane < kDCodes) w.d.code[lane] = (unsigned short)bi_reverse((unsigned)lane, 5), w.d.len[lane] = 5;
+    }
     __syncwarp();
     D9_T(5);  // trees + header
     unsigned long long sa = 0, sb = 0;  // adler32: a = 1 + sum d_i, b = n + sum (n - i) d_i

@@ -1463,11 +1463,20 @@ struct PackPlan {
   int n_groups;
   int group_len[6];         // distinct column lengths, longest first
   int grid[6];
+  bool wide[6];            // four warps per column (few long columns) or one
   long long off_cbuf, off_csize, off_sizes, off_counter, off_scratch, total;
 };
-int ctas_per_sm(int len) {
+int ctas_per_sm(int len, bool wide) {
   const int per = d9::smem_bytes(len) + 1024;  // 1 KB of system-reserved shared memory per CTA
-  return std::max(1, std::min(8, (227 * 1024) / per));  // 8: __launch_bounds__(32 * kWarps, 8) of the kernel
+  // the kernel's __launch_bounds__: 8 CTAs of kWarps warps, or 32 single-warp CTAs
+  return std::max(1, std::min(wide ? 8 : 32, (227 * 1024) / per));
+}
+// One warp per column gives the most columns in flight and the best throughput (measured on 4096 images of 768x512:
+// 39.7 ms against 51.8 ms with four warps per luma column).  Four warps per column shorten a column's critical path
+// (the long chain walks are shared), which is what counts when there are fewer long columns than single-warp slots:
+// one image, small batches.
+bool use_wide(int len, long long streams) {
+  return len > d9::kLongColumn && streams <= (long long)num_sms() * ctas_per_sm(len, false);
 }
 int make_pack_plan(const lrfb_qmf_config* cfg, int batch, PackPlan& P) {
   int rc = lrfb_qmf_layout_query(cfg, &P.L);
@@ -1498,7 +1507,8 @@ int make_pack_plan(const lrfb_qmf_config* cfg, int batch, PackPlan& P) {
     long long streams = 0;
     for (int mtx = 0; mtx < P.n_mat; ++mtx)
       if (P.len[mtx] == P.group_len[g]) streams += (long long)batch * P.ncols[mtx];
-    P.grid[g] = (int)std::min<long long>(streams, (long long)num_sms() * ctas_per_sm(P.group_len[g]));
+    P.wide[g] = use_wide(P.group_len[g], streams);
+    P.grid[g] = (int)std::min<long long>(streams, (long long)num_sms() * ctas_per_sm(P.group_len[g], P.wide[g]));
     scratch = std::max(scratch, P.grid[g] * d9::scratch_per_cta(P.group_len[g]));
   }
   auto up = [](long long v) { return (v + 255) & ~255ll; };
@@ -1550,14 +1560,22 @@ LRFB_EXPORT int32_t lrfb_qmf_pack_device(const lrfb_qmf_config* cfg, int32_t bat
     K.scratch = ws + P.off_scratch;
     K.counter = reinterpret_cast<int*>(ws + P.off_counter) + g;
     const int smem = d9::smem_bytes(K.len);
+    const bool wide = P.wide[g];
 #ifndef LRFB_SIM
-    if (smem > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(d9::deflate9_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      if (e != cudaSuccess) return fail((int)e, "deflate9 shared memory %d: %s", smem, cudaGetErrorString(e));
+    {
+      const void* fn = wide ? (const void*)d9::deflate9_kernel<d9::kWarps> : (const void*)d9::deflate9_kernel<1>;
+      if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return fail((int)e, "deflate9 shared memory %d: %s", smem, cudaGetErrorString(e));
+      }
+      cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     }
-    cudaFuncSetAttribute(d9::deflate9_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 #endif
-    LRFB_LAUNCH(d9::deflate9_kernel, dim3(P.grid[g]), dim3(32 * d9::kWarps), smem, st, K);
+    if (wide) {
+      LRFB_LAUNCH(d9::deflate9_kernel<d9::kWarps>, dim3(P.grid[g]), dim3(32 * d9::kWarps), smem, st, K);
+    } else {
+      LRFB_LAUNCH(d9::deflate9_kernel<1>, dim3(P.grid[g]), dim3(32), smem, st, K);
+    }
     if ((rc = check_launch("deflate9_kernel"))) return rc;
   }
   d9::FrameParams F;
@@ -1598,8 +1616,8 @@ LRFB_EXPORT int32_t lrfb_qmf_encode_bytes_host(lrfb_ctx* c, const lrfb_qmf_confi
   int rc;
   if ((rc = lrfb_qmf_layout_query(cfg, &L))) return rc;
   const size_t img_bytes = (size_t)3 * cfg->height * cfg->width * (cfg->input_dtype == LRFB_U8 ? 1 : 4);
-  // four times the chunk of the records pipeline: the deflate launches need a few thousand columns to fill the GPU
-  // (measured on 4096 images of 768x512: 12.7 Gpixel/s at 256 MiB, 13.9 at 512 MiB, 14.7 at 1 GiB, 13.1 at 2 GiB)
+  // four times the chunk of the records pipeline: the deflate launches want a few thousand columns to fill the GPU
+  // (measured on 4096 images of 768x512, host images -> streams: 16.1 Gpixel/s at 512 MiB, 15.9 at 1 GiB, 14.2 at 2 GiB)
   const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)batch, 4 * c->chunk_bytes / std::max<size_t>(img_bytes, 1)));
   if ((rc = lrfb_qmf_workspace_query(cfg, chunk, &m))) return rc;
   int64_t ws_need = m.total_bytes;

@@ -139,3 +139,20 @@ def test_encode_bytes_host_pipeline_ragged_chunks():
     finally:
         lib.lrfb_ctx_destroy(ctx)
     assert compression.qmf_encode_batch(imgs, quality=12) == want
+
+
+@pytest.mark.gpu
+def test_device_packer_large_batch_single_warp_columns():
+    """More long columns than single-warp slots: the launch takes one warp per column (the small batches above take four
+    warps per long column).  Real factors of distinct images, compared with the native host packer (zlib)."""
+    from oracle import qmf_port as port
+
+    H, W, B = 512, 768, 400
+    pool = torch.stack([port.s_nat(3000 + i, H, W) for i in range(8)])
+    imgs = pool[torch.arange(B) % 8].cuda().contiguous()
+    records, lay, meta = compression.qmf_encode_batch(imgs, quality=7, return_records=True)
+    rolled = records.clone()
+    rolled[B // 2:] = torch.roll(records[B // 2:], 17, dims=1)  # a second family of columns: shifted records
+    cfg, _ = compression.resolve_plan(H, W, None, 7, "YCbCr", (0.5, 0.5), (8, 8), (-16, 15), 10)
+    want = compression.pack_records(rolled.cpu().numpy(), cfg, lay, meta)
+    assert compression.pack_records_device(rolled, cfg, lay, meta) == want

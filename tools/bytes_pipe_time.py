@@ -12,7 +12,7 @@ h_in = torch.empty((B, 3, H, W), dtype=torch.uint8, pin_memory=True)
 h_in.copy_(pool[torch.arange(B) % D])
 cfg, lay = compression.resolve_plan(H, W, None, 7, "YCbCr", (0.5, 0.5), (8, 8), (-16, 15), 10)
 mj = packing.dict_to_bytes(compression._metadata(torch.uint8, "YCbCr", True, (-16, 15), (8, 8), lay))
-lib = _cabi.lib()
+lib = _cabi.bind(C.CDLL(os.environ["LRFB_OUT"])) if os.environ.get("LRFB_OUT") else _cabi.lib()
 cap = B * int(lib.lrfb_qmf_pack_bound(C.byref(cfg), len(mj)))
 blob = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
 offs = torch.zeros(B + 1, dtype=torch.int64, pin_memory=True)

@@ -16,7 +16,8 @@ cfg, lay = compression.resolve_plan(H, W, None, 7, "YCbCr", (0.5, 0.5), (8, 8), 
 meta = compression._metadata(torch.uint8, "YCbCr", True, (-16, 15), (8, 8), lay)
 plan = compression.EncodePlan(cfg, lay, B, imgs.device)
 rec = plan.run(imgs).clone()
-lib = _cabi.lib()
+import os as _os
+lib = _cabi.bind(C.CDLL(_os.environ["LRFB_OUT"])) if _os.environ.get("LRFB_OUT") else _cabi.lib()
 mj = packing.dict_to_bytes(meta)
 wsb = int(lib.lrfb_qmf_pack_device_workspace(C.byref(cfg), B))
 cap = B * int(lib.lrfb_qmf_pack_bound(C.byref(cfg), len(mj)))
