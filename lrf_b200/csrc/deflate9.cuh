@@ -382,7 +382,7 @@ __host__ __device__ inline int smem_region(int len) {
   const int a = 2 * pad_len(len), b = kTreePad + ((len + 32 + 15) & ~15);
   return a > b ? a : b;
 }
-__host__ __device__ inline int smem_bytes(int len) { return smem_data(len) + kFreqPad + kCntBytes + kTaskBytes + smem_region(len); }
+__host__ __device__ inline int smem_bytes(int len) { return smem_data(len) + kFreqPad + kTaskBytes + smem_region(len); }  // the sort's counters live in the frequency area
 
 #ifdef D9_PROF
 __device__ unsigned long long g_d9_prof[16];
@@ -527,9 +527,10 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 32 : 8) deflate9_kernel(Par
   unsigned char* data = smem;
   const unsigned* data32 = reinterpret_cast<const unsigned*>(smem);
   unsigned char* freq_mem = smem + smem_data(n);
-  unsigned short* cnt = reinterpret_cast<unsigned short*>(freq_mem + kFreqPad);  // [256] low digit, [128] high digit
-  Task* task = reinterpret_cast<Task*>(freq_mem + kFreqPad + kCntBytes);
-  unsigned char* region = freq_mem + kFreqPad + kCntBytes + kTaskBytes;
+  static_assert(kCntBytes <= kFreqPad, "the sort's counters borrow the frequency area");
+  unsigned short* cnt = reinterpret_cast<unsigned short*>(freq_mem);  // [256] low digit, [128] high digit; dead before the parse
+  Task* task = reinterpret_cast<Task*>(freq_mem + kFreqPad);
+  unsigned char* region = freq_mem + kFreqPad + kTaskBytes;
   unsigned short* A = reinterpret_cast<unsigned short*>(region);  // positions sorted by (hash, position)
   unsigned char* scr = P.scratch + (long long)blockIdx.x * scratch_per_cta(n);
   unsigned short* B = reinterpret_cast<unsigned short*>(scr);                // sort ping-pong, dead once RC is written
@@ -573,7 +574,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 32 : 8) deflate9_kernel(Par
       for (int i = lane; i < n; i += 32) data[i] = src[i];
     }
     for (int i = n + lane; i < smem_data(n); i += 32) data[i] = 0;
-    for (int i = lane; i < (kFreqPad + kCntBytes) / 4; i += 32) reinterpret_cast<unsigned*>(freq_mem)[i] = 0;  // not the task
+    for (int i = lane; i < kCntBytes / 4; i += 32) reinterpret_cast<unsigned*>(freq_mem)[i] = 0;
     __syncwarp();
 
     // ---- positions sorted by (hash, position): two stable counting passes (8 + 7 bits) ----------------------------
@@ -663,6 +664,8 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 32 : 8) deflate9_kernel(Par
     }
     __syncwarp();
 
+    for (int i = lane; i < kFreqPad / 4; i += 32) reinterpret_cast<unsigned*>(freq_mem)[i] = 0;  // symbol frequencies
+    __syncwarp();
     D9_T(1);  // ranks
     // ---- deflate_slow ------------------------------------------------------------------------------------------------
     unsigned short* lfreq = reinterpret_cast<unsigned short*>(freq_mem);
