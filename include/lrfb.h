@@ -194,7 +194,7 @@ int32_t lrfb_qmf_pack_host(const lrfb_qmf_config* cfg, int32_t batch, const int8
  * image i's stream is d_blob[d_offsets[i] .. d_offsets[i+1]) (d_offsets: batch + 1 int64 in device memory, streams packed
  * back to back).  blob_capacity >= batch * lrfb_qmf_pack_bound(cfg, metadata_len) always suffices; when
  * d_offsets[batch] > blob_capacity the images that did not fit are not written (check after the copy back).
- * Columns longer than 16 382 bytes (one deflate block, no window slide) return LRFB_E_UNSUPPORTED and
+ * Columns longer than 65 024 bytes (zlib's 64 KB window would slide) return LRFB_E_UNSUPPORTED and
  * lrfb_qmf_pack_device_workspace returns -1: use lrfb_qmf_pack_host for those shapes. */
 int64_t lrfb_qmf_pack_device_workspace(const lrfb_qmf_config* cfg, int32_t batch);
 int32_t lrfb_qmf_pack_device(const lrfb_qmf_config* cfg, int32_t batch, const int8_t* d_records,

@@ -55,7 +55,7 @@ def pack_records(records: np.ndarray, cfg, lay, meta: dict, threads: int = 0) ->
 
 
 def device_packer_supported(cfg, batch: int = 1) -> bool:
-    """True when every factor column of this shape fits the device deflate (at most 16 382 bytes per column)."""
+    """True when every factor column of this shape fits the device deflate (at most 65 024 bytes per column)."""
     return int(_cabi.lib().lrfb_qmf_pack_device_workspace(C.byref(cfg), batch)) > 0
 
 
@@ -288,7 +288,7 @@ def qmf_encode_batch(images: torch.Tensor, rank=None, quality=None, color_space:
         if device_packer_supported(cfg, B):
             return pack_records_device(records, cfg, lay, meta)
         host = records.cpu().numpy()
-    return pack_records(host, cfg, lay, meta)  # columns above 16 382 bytes: zlib on the host thread pool
+    return pack_records(host, cfg, lay, meta)  # columns above 65 024 bytes: zlib on the host thread pool
 
 
 def qmf_encode(image: torch.Tensor, rank=None, quality=None, color_space: str = "YCbCr",

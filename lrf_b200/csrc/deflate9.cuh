@@ -4,8 +4,9 @@
 // zlib is a third-party dependency of the reference (CPython's zlib module, zlib 1.2.x / 1.3: the deflate
 // algorithm at level 9 has been output-stable across those versions for inputs of one block); its published algorithm is
 // restated here: deflate_slow (lazy matching, good_length 32, max_lazy 258, nice_length 258, max_chain 4096,
-// 15-bit rolling hash of 3 bytes, TOO_FAR 4096), one block per stream (inputs of at most kMaxLen bytes never fill the
-// 16 383-symbol literal buffer and never slide the 32 KB window), trees.c's heap-ordered Huffman construction with its
+// 15-bit rolling hash of 3 bytes, TOO_FAR 4096, matches no farther than MAX_DIST = 32 506), a block flushed whenever the
+// symbol buffer holds 16 383 entries (columns up to 16 382 bytes are one block), no window slide (inputs of at most kMaxLen
+// = 65 024 bytes sit in zlib's 64 KB window at once), trees.c's heap-ordered Huffman construction with its
 // depth tie-break and overflow repair, the run-length coded tree header, the stored / static / dynamic choice, and
 // the zlib wrapper (78 DA ... adler32).  Parity anchor: the system zlib itself (tests/test_deflate9.py compares every
 // stream byte for byte).
@@ -24,7 +25,10 @@
 namespace lrfb {
 namespace d9 {
 
-constexpr int kMaxLen = 16382;  // longest column the device path takes (one block, no window slide, no buffer flush)
+constexpr int kMaxLen = 65024;       // longest column the device path takes: the whole input sits in zlib's 64 KB window, which never slides
+constexpr int kOneBlock = 16382;     // columns up to here are one deflate block (fewer symbols than the 16 383-entry buffer)
+constexpr int kBlockSymbols = 16383; // zlib flushes a block when its symbol buffer holds lit_bufsize - 1 entries
+constexpr int kMaxDist = 32506;      // w_size - MIN_LOOKAHEAD: the farthest match zlib takes
 constexpr int kHeap = 573;      // 2 * L_CODES + 1
 constexpr int kLCodes = 286, kDCodes = 30, kBLCodes = 19;
 
@@ -255,9 +259,18 @@ __host__ __device__ inline void scan_tree(const Tree& t, Work& w, int max_code) 
 // LSB-first bit writer over zero-initialised 32-bit words (the staged output).  Serial use only.
 struct BitW {
   unsigned* words;
-  unsigned pos;  // in bits
+  unsigned pos;     // in bits
+  int in_global;    // the words are in global memory next to atomicOr traffic: go through the atomics too (L1 may be stale)
   __host__ __device__ inline void put(unsigned v, int nbits) {
     const unsigned wi = pos >> 5, sh = pos & 31;
+#if defined(__CUDA_ARCH__)
+    if (in_global) {
+      atomicOr(words + wi, v << sh);
+      if (sh + nbits > 32) atomicOr(words + wi + 1, v >> (32 - sh));
+      pos += nbits;
+      return;
+    }
+#endif
     words[wi] |= v << sh;
     if (sh + nbits > 32) words[wi + 1] |= v >> (32 - sh);
     pos += nbits;
@@ -294,7 +307,7 @@ __host__ __device__ inline void send_tree(const Tree& t, const Work& w, int max_
 // counts (END_BLOCK included), internal nodes and b.freq are cleared here.  Returns the block type (0 stored, 1 static,
 // 2 dynamic); for 1 and 2 the 3 header bits (+ the tree header) are written at o and l/d code + len describe the
 // code to use for every symbol.
-__host__ __device__ inline int begin_block(Work& w, int stored_len, BitW& o, bool fill_static = true) {
+__host__ __device__ inline int begin_block(Work& w, int stored_len, BitW& o, bool fill_static = true, int last = 1) {
   w.opt_len = 0, w.static_len = 0;
   for (int i = 0; i < kBLCodes; ++i) w.b.freq[i] = 0;
   build_tree(w.l, w);
@@ -311,13 +324,13 @@ __host__ __device__ inline int begin_block(Work& w, int stored_len, BitW& o, boo
   if (static_lenb <= opt_lenb) opt_lenb = static_lenb;
   if ((unsigned)stored_len + 4 <= opt_lenb) return 0;
   if (static_lenb == opt_lenb) {
-    o.put((1 << 1) + 1, 3);
+    o.put((1 << 1) + (unsigned)last, 3);
     if (!fill_static) return 1;  // the caller writes the fixed code (the kernel does it on all lanes)
     for (int n = 0; n < kLCodes; ++n) w.l.code[n] = (unsigned short)bi_reverse(static_lcode(n), static_llen(n)), w.l.len[n] = (unsigned char)static_llen(n);
     for (int n = 0; n < kDCodes; ++n) w.d.code[n] = (unsigned short)bi_reverse((unsigned)n, 5), w.d.len[n] = 5;
     return 1;
   }
-  o.put((2 << 1) + 1, 3);
+  o.put((2 << 1) + (unsigned)last, 3);
   o.put((unsigned)(w.l.max_code + 1 - 257), 5);
   o.put((unsigned)(w.d.max_code + 1 - 1), 5);
   o.put((unsigned)(max_blindex + 1 - 4), 4);
@@ -378,9 +391,13 @@ __host__ __device__ inline int pad_len(int len) { return (len + 63) & ~63; }
 __host__ __device__ inline long long scratch_per_cta(int len) { return 7ll * pad_len(len); }
 __host__ __device__ inline int smem_data(int len) { return (len + 16 + 15) & ~15; }
 constexpr int kFreqPad = (kFreqBytes + 15) & ~15, kCntBytes = 2 * (256 + 128), kTaskBytes = 64, kTreePad = (kTreeBytes + 15) & ~15;
+__host__ __device__ inline int slot_bytes(int len) { return (len + 64 + 15) & ~15; }  // output slot of a column (stored blocks: +5 each)
+// the sorted positions A (2 bytes each) share their region with the Huffman scratch and the staged output of a one-block
+// column (both are needed only after the parse); a column of several blocks flushes blocks while A is alive, so its
+// Huffman scratch sits behind A and its output is staged in the column's global slot
 __host__ __device__ inline int smem_region(int len) {
-  const int a = 2 * pad_len(len), b = kTreePad + ((len + 32 + 15) & ~15);
-  return a > b ? a : b;
+  const int a = 2 * pad_len(len), b = kTreePad + slot_bytes(len);
+  return len > kOneBlock ? a + kTreePad : (a > b ? a : b);
 }
 __host__ __device__ inline int smem_bytes(int len) { return smem_data(len) + kFreqPad + kTaskBytes + smem_region(len); }  // the sort's counters live in the frequency area
 
@@ -419,7 +436,8 @@ __device__ __forceinline__ unsigned ld4(const unsigned* w, int off) {
 // end of the input) ends the walk — zlib stops there too — and candidates beyond it never matter because no length exceeds it.
 __device__ __forceinline__ void walk_chain(const unsigned char* data, const unsigned* data32, const unsigned short* A,
                                            int p, int rank, int left, int maxlen, int w, int nw, int* nice_idx, int lane,
-                                           int& best, int& bidx) {
+                                           int& best, int& bidx, const int limit) {
+  // limit: zlib ends the walk at the first candidate farther than MAX_DIST; 0 (NIL) for every column of one block
   // filter offsets f1, f2 start at 3, 4 and then follow the survivors: where the last ones parted from the string at p
   // the next chain members usually do too (1 % get through instead of 2.7 %)
   unsigned ex = 0, exm = 0;
@@ -452,7 +470,7 @@ __device__ __forceinline__ void walk_chain(const unsigned char* data, const unsi
       q[j] = idx < left ? A[rank - 1 - idx] : 0;
     }
 #pragma unroll
-    for (int j = 0; j < kWide; ++j) pm[j] = __ballot_sync(0xffffffffu, q[j] != 0 && filter(q[j]));
+    for (int j = 0; j < kWide; ++j) pm[j] = __ballot_sync(0xffffffffu, q[j] > limit && filter(q[j]));
     bool done = false;
 #pragma unroll
     for (int j = 0; j < kWide; ++j) {
@@ -497,9 +515,9 @@ __device__ __forceinline__ void walk_chain(const unsigned char* data, const unsi
         for (int j2 = j + 1; j2 < kWide; ++j2) more |= pm[j2] != 0;
         if (more) {  // the rest of this step is re-filtered against the new best / the new offsets
           set_filter(), dirty = false;
-          mset = __ballot_sync(0xffffffffu, lane > src && q[j] != 0 && filter(q[j]));
+          mset = __ballot_sync(0xffffffffu, lane > src && q[j] > limit && filter(q[j]));
 #pragma unroll
-          for (int j2 = j + 1; j2 < kWide; ++j2) pm[j2] = __ballot_sync(0xffffffffu, q[j2] != 0 && filter(q[j2]));
+          for (int j2 = j + 1; j2 < kWide; ++j2) pm[j2] = __ballot_sync(0xffffffffu, q[j2] > limit && filter(q[j2]));
         }
       }
       if (done) break;
@@ -519,7 +537,76 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
   return v;
 }
 
-template <int NW>  // warps per column: 4 for long columns (shared chain walks), 1 for short ones (more columns per SM)
+// _tr_flush_block: trees and header on lane 0, symbols on all lanes (prefix sum of code lengths, atomicOr into the output),
+// or LEN / NLEN and the bytes for a stored block; then init_block.  Out of line: the parse loop calls it from three places.
+struct BlockOut {
+  unsigned* words;         // zero-initialised output (shared for one-block columns, the global slot otherwise)
+  Work* w;
+  unsigned char* freq_mem;
+  const unsigned char* data;
+  const unsigned short* sym_d;
+  const unsigned char* sym_l;
+  unsigned bitpos;
+  int block_start;
+  int in_global;
+};
+__device__ __forceinline__ void flush_block_body(BlockOut& b, int end, int last, int ns, int lane) {
+  Work& w = *b.w;
+  unsigned* words = b.words;
+  unsigned bitpos = b.bitpos;
+  const int stored_len = end - b.block_start;
+  int type = 0;
+  if (lane == 0) {
+    w.l.freq[256] = 1;
+    BitW o{words, bitpos, b.in_global};
+    type = begin_block(w, stored_len, o, false, last);
+    if (type == 0) o.put((unsigned)last, 3), o.pos = (o.pos + 7u) & ~7u;
+    bitpos = o.pos;
+  }
+  type = __shfl_sync(0xffffffffu, type, 0);
+  bitpos = __shfl_sync(0xffffffffu, bitpos, 0);
+  if (type == 1) {  // fixed Huffman code
+    for (int c = lane; c < kLCodes; c += 32) w.l.code[c] = (unsigned short)bi_reverse(static_lcode(c), static_llen(c)), w.l.len[c] = (unsigned char)static_llen(c);
+    if (lane < kDCodes) w.d.code[lane] = (unsigned short)bi_reverse((unsigned)lane, 5), w.d.len[lane] = 5;
+  }
+  __syncwarp();
+  if (type == 0) {  // stored block: LEN, NLEN, the bytes
+    unsigned char* ob = reinterpret_cast<unsigned char*>(words) + (bitpos >> 3);
+    if (lane == 0) ob[0] = (unsigned char)stored_len, ob[1] = (unsigned char)(stored_len >> 8), ob[2] = (unsigned char)~stored_len, ob[3] = (unsigned char)(~stored_len >> 8);
+    for (int i = lane; i < stored_len; i += 32) ob[4 + i] = b.data[b.block_start + i];
+    bitpos += 8u * (4u + (unsigned)stored_len);
+  } else {
+    for (int base = 0; base <= ns; base += 32) {
+      const int i = base + lane;
+      int nb = 0;
+      unsigned long long v = 0;
+      if (i < ns) v = symbol_bits(w, __ldcg(b.sym_d + i), __ldcg(b.sym_l + i), nb);
+      else if (i == ns) v = symbol_bits(w, 0, 256, nb);
+      const int inc = warp_incl_scan(nb, lane);
+      if (nb) {
+        const unsigned pos = bitpos + (unsigned)(inc - nb), wi = pos >> 5, sh = pos & 31;
+        atomicOr(words + wi, (unsigned)(v << sh));
+        const unsigned long long hi = sh ? (v >> (32 - sh)) : (v >> 16 >> 16);
+        if (hi) {
+          atomicOr(words + wi + 1, (unsigned)hi);
+          if (hi >> 32) atomicOr(words + wi + 2, (unsigned)(hi >> 32));
+        }
+      }
+      bitpos += (unsigned)__shfl_sync(0xffffffffu, inc, 31);
+    }
+  }
+  __syncwarp();
+  if (!last) {  // init_block
+    for (int i = lane; i < kFreqPad / 4; i += 32) reinterpret_cast<unsigned*>(b.freq_mem)[i] = 0;
+    __syncwarp();
+  }
+  b.bitpos = bitpos, b.block_start = end;
+}
+__device__ __noinline__ void flush_block_out(BlockOut& b, int end, int last, int ns, int lane) { flush_block_body(b, end, last, ns, lane); }
+
+// NW warps per column: 4 shorten a long column's critical path (shared chain walks), 1 puts more columns on an SM.
+// MULTI: columns above kOneBlock bytes (several deflate blocks, flushed in mid-parse).
+template <int NW, bool MULTI>
 __global__ void __launch_bounds__(32 * NW, NW == 1 ? 32 : 8) deflate9_kernel(Params P) {
   LRFB_DYN_SMEM(smem);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -551,7 +638,8 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 32 : 8) deflate9_kernel(Par
         if (*reinterpret_cast<volatile int*>(&task->cmd) == 2) break;
         const int tp = task->p, tmax = task->maxlen, trank = task->rank, tleft = task->left;
         int best = task->best, bidx = -1;
-        walk_chain(data, data32, A, tp, trank, tleft, tmax, warp, NW, &task->nice_idx, lane, best, bidx);
+        walk_chain(data, data32, A, tp, trank, tleft, tmax, warp, NW, &task->nice_idx, lane, best, bidx,
+                   MULTI && tp > kMaxDist ? tp - kMaxDist : 0);
         if (bidx >= 0 && lane == 0) atomicMax(&task->key, ((unsigned)best << 12) | (unsigned)(4095 - bidx));
         __syncthreads();
       }
@@ -671,6 +759,23 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 32 : 8) deflate9_kernel(Par
     unsigned short* lfreq = reinterpret_cast<unsigned short*>(freq_mem);
     unsigned short* dfreq = lfreq + kHeap;
     int strstart = 0, lookahead = n, match_length = 2, match_start = 0, match_available = 0, ns = 0;
+    // ---- block output: _tr_flush_block.  One block per column up to kOneBlock bytes; longer columns flush whenever the
+    // symbol buffer holds 16 383 entries, as zlib does, with the Huffman scratch behind A and the output in the global slot
+    constexpr bool multi = MULTI;
+    unsigned* words = multi ? reinterpret_cast<unsigned*>(dst) : reinterpret_cast<unsigned*>(region + kTreePad);
+    Work w;
+    work_bind(w, freq_mem, multi ? region + 2 * lp : region);
+    const unsigned bitpos = 16;
+    if (multi) {
+      for (int i = lane; i < slot_bytes(n) / 4; i += 32) words[i] = i == 0 ? 0xDA78u : 0u;
+      __syncwarp();
+    }
+    BlockOut bo{words, &w, freq_mem, data, sym_d, sym_l, bitpos, 0, multi ? 1 : 0};
+    auto flush_block = [&](int end, int last) {
+      if (MULTI) flush_block_out(bo, end, last, ns, lane);  // three call sites in the parse loop
+      else flush_block_body(bo, end, last, ns, lane);
+      ns = 0;
+    };
     // rank | candidates of 128 positions ahead of the parse live in four registers per lane; the far half is
     // requested from L2 64 positions before it is needed
     int wbase = -1000000;
@@ -708,7 +813,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 32 : 8) deflate9_kernel(Par
             task->key = 0, task->nice_idx = 0x7fffffff;
           }
           __syncthreads();
-          walk_chain(data, data32, A, p, rank, left, maxlen, 0, NW, &task->nice_idx, lane, best, bidx);
+          walk_chain(data, data32, A, p, rank, left, maxlen, 0, NW, &task->nice_idx, lane, best, bidx, MULTI && p > kMaxDist ? p - kMaxDist : 0);
           if (bidx >= 0 && lane == 0) atomicMax(&task->key, ((unsigned)best << 12) | (unsigned)(4095 - bidx));
           __syncthreads();
           const unsigned key = *reinterpret_cast<volatile unsigned*>(&task->key);
@@ -718,7 +823,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 32 : 8) deflate9_kernel(Par
           D9_C(8, 1);
           D9_C(9, left);
         } else {
-          walk_chain(data, data32, A, p, rank, left, maxlen, 0, 1, nullptr, lane, best, bidx);
+          walk_chain(data, data32, A, p, rank, left, maxlen, 0, 1, nullptr, lane, best, bidx, MULTI && p > kMaxDist ? p - kMaxDist : 0);
           D9_T(4);  // short walks
           D9_C(10, 1);
           D9_C(11, left);
@@ -736,13 +841,22 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 32 : 8) deflate9_kernel(Par
         ++ns;
         lookahead -= prev_length - 1, strstart += prev_length - 1;
         match_available = 0, match_length = 2;
+        if (MULTI && ns == kBlockSymbols) {
+          __syncwarp();
+          flush_block(strstart, 0);
+        }
       } else if (match_available) {
         if (lane == 0) {
           const unsigned c = data[strstart - 1];
           __stcg(sym_d + ns, (unsigned short)0), __stcg(sym_l + ns, (unsigned char)c);
           lfreq[c]++;
         }
-        ++ns, ++strstart, --lookahead;
+        ++ns;
+        if (MULTI && ns == kBlockSymbols) {  // zlib flushes before it steps over the pending byte
+          __syncwarp();
+          flush_block(strstart, 0);
+        }
+        ++strstart, --lookahead;
       } else {
         match_available = 1, ++strstart, --lookahead;
       }
@@ -759,73 +873,27 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 32 : 8) deflate9_kernel(Par
     if (lane == 0) task->cmd = 2;
     __syncthreads();  // the helper warps leave; A may now be overwritten
 
-    // ---- trees and block header (lane 0), then the symbols on all lanes ----------------------------------------------
-    unsigned* words = reinterpret_cast<unsigned*>(region + kTreePad);
-    for (int i = lane; i < ((n + 32 + 15) & ~15) / 4; i += 32) words[i] = 0;
-    __syncwarp();
-    Work w;
-    work_bind(w, freq_mem, region);
-    int type = 0;
-    unsigned bitpos = 16;
-    if (lane == 0) {
-      lfreq[256] = 1;
-      words[0] = 0xDA78u;
-      BitW o{words, 16};
-      type = begin_block(w, n, o, false);
-      bitpos = o.pos;
+    // ---- the last block (trees and header on lane 0, symbols on all lanes), adler32, copy out -------------------------
+    if (!multi) {
+      for (int i = lane; i < slot_bytes(n) / 4; i += 32) words[i] = i == 0 ? 0xDA78u : 0u;
+      __syncwarp();
     }
-    type = __shfl_sync(0xffffffffu, type, 0);
-    bitpos = __shfl_sync(0xffffffffu, bitpos, 0);
-    if (type == 1) {  // fixed Huffman code
-      for (int c = lane; c < kLCodes; c += 32) w.l.code[c] = (unsigned short)bi_reverse(static_lcode(c), static_llen(c)), w.l.len[c] = (unsigned char)static_llen(c);
-      if (lane < kDCodes) w.d.code[lane] = (unsigned short)bi_reverse((unsigned)lane, 5), w.d.len[lane] = 5;
-    }
-    __syncwarp();
-    D9_T(5);  // trees + header
+    flush_block(strstart, 1);
+    D9_T(5);  // trees + header + symbols
     unsigned long long sa = 0, sb = 0;  // adler32: a = 1 + sum d_i, b = n + sum (n - i) d_i
     for (int i = lane; i < n; i += 32) sa += data[i], sb += (unsigned long long)(n - i) * data[i];
 #pragma unroll
     for (int o = 16; o; o >>= 1) sa += __shfl_xor_sync(0xffffffffu, sa, o), sb += __shfl_xor_sync(0xffffffffu, sb, o);
     const unsigned ad_a = (unsigned)((1 + sa) % 65521ull), ad_b = (unsigned)((n + sb) % 65521ull);
-    int total;
-    if (type == 0) {  // stored block
-      if (lane == 0) {
-        dst[0] = 0x78, dst[1] = 0xDA, dst[2] = 1;
-        dst[3] = (unsigned char)n, dst[4] = (unsigned char)(n >> 8), dst[5] = (unsigned char)~n, dst[6] = (unsigned char)(~n >> 8);
-      }
-      for (int i = lane; i < n; i += 32) dst[7 + i] = data[i];
-      total = 7 + n;
-      if (lane == 0) dst[total] = (unsigned char)(ad_b >> 8), dst[total + 1] = (unsigned char)ad_b, dst[total + 2] = (unsigned char)(ad_a >> 8), dst[total + 3] = (unsigned char)ad_a;
-      total += 4;
-    } else {
-      for (int base = 0; base <= ns; base += 32) {
-        const int i = base + lane;
-        int nb = 0;
-        unsigned long long v = 0;
-        if (i < ns) v = symbol_bits(w, __ldcg(sym_d + i), __ldcg(sym_l + i), nb);
-        else if (i == ns) v = symbol_bits(w, 0, 256, nb);
-        const int inc = warp_incl_scan(nb, lane);
-        if (nb) {
-          const unsigned pos = bitpos + (unsigned)(inc - nb), wi = pos >> 5, sh = pos & 31;
-          atomicOr(words + wi, (unsigned)(v << sh));
-          const unsigned long long hi = sh ? (v >> (32 - sh)) : (v >> 16 >> 16);
-          if (hi) {
-            atomicOr(words + wi + 1, (unsigned)hi);
-            if (hi >> 32) atomicOr(words + wi + 2, (unsigned)(hi >> 32));
-          }
-        }
-        bitpos += (unsigned)__shfl_sync(0xffffffffu, inc, 31);
-      }
-      __syncwarp();
-      total = (int)((bitpos + 7) >> 3);
-      if (lane == 0) {
-        unsigned char* ob = reinterpret_cast<unsigned char*>(words);
-        ob[total] = (unsigned char)(ad_b >> 8), ob[total + 1] = (unsigned char)ad_b, ob[total + 2] = (unsigned char)(ad_a >> 8), ob[total + 3] = (unsigned char)ad_a;
-      }
-      total += 4;
-      __syncwarp();
-      for (int i = lane; i < (total + 3) / 4; i += 32) reinterpret_cast<unsigned*>(dst)[i] = words[i];
+    int total = (int)((bo.bitpos + 7) >> 3);
+    if (lane == 0) {
+      unsigned char* ob = reinterpret_cast<unsigned char*>(words);
+      ob[total] = (unsigned char)(ad_b >> 8), ob[total + 1] = (unsigned char)ad_b, ob[total + 2] = (unsigned char)(ad_a >> 8), ob[total + 3] = (unsigned char)ad_a;
     }
+    total += 4;
+    __syncwarp();
+    if (!multi)
+      for (int i = lane; i < (total + 3) / 4; i += 32) reinterpret_cast<unsigned*>(dst)[i] = words[i];
     D9_T(6);  // symbols + copy out
     if (lane == 0) *dsize = (unsigned)total;
     __syncwarp();
@@ -951,11 +1019,37 @@ inline long long deflate9_serial(const unsigned char* in, int n, unsigned char* 
   std::vector<unsigned char> fm(kFreqBytes, 0), tm(kTreeBytes, 0);
   Work w;
   work_bind(w, fm.data(), tm.data());
-  int ns = 0;
+  std::vector<unsigned> words((n + 256) / 4 + 8, 0);
+  BitW o{words.data(), 16, 0};
+  words[0] = 0xDA78u;
+  int ns = 0, block_start = 0;
+  auto flush_block = [&](int end, int last) {  // _tr_flush_block(window + block_start, end - block_start, last)
+    w.l.freq[256] = 1;
+    const int stored_len = end - block_start;
+    const int type = begin_block(w, stored_len, o, true, last);
+    if (type == 0) {
+      o.put((unsigned)last, 3);
+      o.pos = (o.pos + 7) & ~7u;
+      unsigned char* ob = reinterpret_cast<unsigned char*>(words.data()) + (o.pos >> 3);
+      ob[0] = (unsigned char)stored_len, ob[1] = (unsigned char)(stored_len >> 8), ob[2] = (unsigned char)~stored_len, ob[3] = (unsigned char)(~stored_len >> 8);
+      if (stored_len) memcpy(ob + 4, in + block_start, stored_len);
+      o.pos += 8u * (4 + stored_len);
+    } else {
+      for (int i = 0; i <= ns; ++i) {
+        int nb;
+        const unsigned long long v = i < ns ? symbol_bits(w, sd[i], sl[i], nb) : symbol_bits(w, 0, 256, nb);
+        o.put((unsigned)v, nb > 32 ? 32 : nb);
+        if (nb > 32) o.put((unsigned)(v >> 32), nb - 32);
+      }
+    }
+    memset(fm.data(), 0, fm.size());
+    ns = 0, block_start = end;
+  };
   auto tally = [&](unsigned dist, unsigned lc) {
     sd[ns] = (unsigned short)dist, sl[ns] = (unsigned char)lc, ++ns;
     if (dist == 0) w.l.freq[lc]++;
     else w.l.freq[length_code((int)lc) + 257]++, w.d.freq[dist_code((int)dist - 1)]++;
+    return ns == kBlockSymbols;
   };
   int strstart = 0, lookahead = n, match_length = 2, prev_length, match_start = 0, prev_match, match_available = 0;
   long long np = 0;
@@ -967,9 +1061,10 @@ inline long long deflate9_serial(const unsigned char* in, int n, unsigned char* 
       head[h] = (unsigned short)strstart;
     }
     prev_length = match_length, prev_match = match_start, match_length = 2;
-    if (hash_head != 0 && prev_length < 258) {
+    if (hash_head != 0 && prev_length < 258 && strstart - hash_head <= kMaxDist) {
       unsigned chain = prev_length >= 32 ? 1024 : 4096;
       int best = prev_length, nice = std::min(258, lookahead), cur = hash_head;
+      const int limit = strstart > kMaxDist ? strstart - kMaxDist : 0;
       do {
         ++np;
         int len = 0;
@@ -978,13 +1073,13 @@ inline long long deflate9_serial(const unsigned char* in, int n, unsigned char* 
           match_start = cur, best = len;
           if (len >= nice) break;
         }
-      } while ((cur = prev[cur & 32767]) > 0 && --chain != 0);
+      } while ((cur = prev[cur & 32767]) > limit && --chain != 0);
       match_length = std::min(best, lookahead);
       if (match_length == 3 && strstart - match_start > 4096) match_length = 2;
     }
     if (prev_length >= 3 && match_length <= prev_length) {
       const int max_insert = strstart + lookahead - 3;
-      tally((unsigned)(strstart - 1 - prev_match), (unsigned)(prev_length - 3));
+      const bool bflush = tally((unsigned)(strstart - 1 - prev_match), (unsigned)(prev_length - 3));
       lookahead -= prev_length - 1;
       prev_length -= 2;
       do {
@@ -995,36 +1090,19 @@ inline long long deflate9_serial(const unsigned char* in, int n, unsigned char* 
         }
       } while (--prev_length != 0);
       match_available = 0, match_length = 2, strstart++;
+      if (bflush) flush_block(strstart, 0);
     } else if (match_available) {
-      tally(0, win[strstart - 1]);
+      if (tally(0, win[strstart - 1])) flush_block(strstart, 0);
       strstart++, lookahead--;
     } else {
       match_available = 1, strstart++, lookahead--;
     }
   }
   if (match_available) tally(0, win[strstart - 1]);
-  w.l.freq[256] = 1;
   if (probes) *probes = np;
-  std::vector<unsigned> words((n + 64) / 4 + 8, 0);
-  BitW o{words.data(), 16};
-  words[0] = 0xDA78u;
-  const int type = begin_block(w, n, o);
-  long long nbytes;
-  if (type == 0) {
-    out[0] = 0x78, out[1] = 0xDA, out[2] = 1;
-    out[3] = (unsigned char)n, out[4] = (unsigned char)(n >> 8), out[5] = (unsigned char)~n, out[6] = (unsigned char)(~n >> 8);
-    if (n) memcpy(out + 7, in, n);
-    nbytes = 7 + n;
-  } else {
-    for (int i = 0; i <= ns; ++i) {
-      int nb;
-      const unsigned long long v = i < ns ? symbol_bits(w, sd[i], sl[i], nb) : symbol_bits(w, 0, 256, nb);
-      o.put((unsigned)v, nb > 32 ? 32 : nb);
-      if (nb > 32) o.put((unsigned)(v >> 32), nb - 32);
-    }
-    nbytes = (o.pos + 7) >> 3;
-    memcpy(out, words.data(), nbytes);
-  }
+  flush_block(strstart, 1);
+  long long nbytes = (o.pos + 7) >> 3;
+  memcpy(out, words.data(), nbytes);
   unsigned a = 1, b = 0;
   for (int i = 0; i < n; ++i) a = (a + in[i]) % 65521u, b = (b + a) % 65521u;
   out[nbytes] = (unsigned char)(b >> 8), out[nbytes + 1] = (unsigned char)b, out[nbytes + 2] = (unsigned char)(a >> 8), out[nbytes + 3] = (unsigned char)a;

@@ -1493,7 +1493,7 @@ int make_pack_plan(const lrfb_qmf_config* cfg, int batch, PackPlan& P) {
     if (P.len[mtx] > d9::kMaxLen) return fail(LRFB_E_UNSUPPORTED, "column of %d bytes: the device deflate takes at most %d (use lrfb_qmf_pack_host)", P.len[mtx], d9::kMaxLen);
     if (P.ncols[mtx] > 64) return fail(LRFB_E_UNSUPPORTED, "rank above 64");
     P.col0[mtx] = P.cols_total, P.cols_total += P.ncols[mtx];
-    P.slot[mtx] = (P.len[mtx] + 16 + 15) & ~15;
+    P.slot[mtx] = d9::slot_bytes(P.len[mtx]);
     P.slot_off[mtx] = (int)so, so += (long long)P.ncols[mtx] * P.slot[mtx];
     bool seen = false;
     for (int g = 0; g < P.n_groups; ++g) seen |= P.group_len[g] == P.len[mtx];
@@ -1547,7 +1547,7 @@ LRFB_EXPORT int32_t lrfb_qmf_pack_device(const lrfb_qmf_config* cfg, int32_t bat
     d9::Params K;
     memset(&K, 0, sizeof(K));
     K.rec = reinterpret_cast<const unsigned char*>(d_records), K.rec_stride = P.L.record_bytes;
-    K.len = P.group_len[g], K.slot = (K.len + 16 + 15) & ~15;
+    K.len = P.group_len[g], K.slot = d9::slot_bytes(K.len);
     for (int mtx = 0; mtx < P.n_mat; ++mtx)
       if (P.len[mtx] == K.len) {
         d9::ColSeg& sg = K.seg[K.n_seg++];
@@ -1560,22 +1560,18 @@ LRFB_EXPORT int32_t lrfb_qmf_pack_device(const lrfb_qmf_config* cfg, int32_t bat
     K.scratch = ws + P.off_scratch;
     K.counter = reinterpret_cast<int*>(ws + P.off_counter) + g;
     const int smem = d9::smem_bytes(K.len);
-    const bool wide = P.wide[g];
+    const bool wide = P.wide[g], multi = K.len > d9::kOneBlock;
+    typedef void (*kernel_t)(d9::Params);
+    const kernel_t fn = wide ? (multi ? d9::deflate9_kernel<d9::kWarps, true> : d9::deflate9_kernel<d9::kWarps, false>)
+                             : (multi ? d9::deflate9_kernel<1, true> : d9::deflate9_kernel<1, false>);
 #ifndef LRFB_SIM
-    {
-      const void* fn = wide ? (const void*)d9::deflate9_kernel<d9::kWarps> : (const void*)d9::deflate9_kernel<1>;
-      if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return fail((int)e, "deflate9 shared memory %d: %s", smem, cudaGetErrorString(e));
-      }
-      cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return fail((int)e, "deflate9 shared memory %d: %s", smem, cudaGetErrorString(e));
     }
+    cudaFuncSetAttribute((const void*)fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 #endif
-    if (wide) {
-      LRFB_LAUNCH(d9::deflate9_kernel<d9::kWarps>, dim3(P.grid[g]), dim3(32 * d9::kWarps), smem, st, K);
-    } else {
-      LRFB_LAUNCH(d9::deflate9_kernel<1>, dim3(P.grid[g]), dim3(32), smem, st, K);
-    }
+    LRFB_LAUNCH(fn, dim3(P.grid[g]), dim3(wide ? 32 * d9::kWarps : 32), smem, st, K);
     if ((rc = check_launch("deflate9_kernel"))) return rc;
   }
   d9::FrameParams F;

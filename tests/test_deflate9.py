@@ -44,6 +44,13 @@ def test_serial_restatement_matches_zlib():
     rng = np.random.default_rng(11)
     for data in _streams(rng, 1500, 9000) + [bytes(16382), rng.integers(-16, 16, 16382).astype(np.int8).tobytes()]:
         assert simlib.deflate9_serial(data) == zlib.compress(data, 9), len(data)
+    # several deflate blocks (more than 16 383 symbols), matches limited to MAX_DIST, up to the longest column taken
+    for n in (16383, 16384, 20000, 43776, 65024):
+        t = np.arange(n)
+        for a in (rng.integers(-16, 16, n), rng.integers(0, 256, n), np.zeros(n), np.rint(9 * np.sin(t * 0.003) + (rng.integers(0, 4, n) == 0)),
+                  np.where(t < 40000, (t * 7 + t // 9) % 11, 0) + np.where(t >= 40000, ((t - 40000) * 7 + (t - 40000) // 9) % 11, 0)):
+            data = a.astype(np.int8).tobytes()
+            assert simlib.deflate9_serial(data) == zlib.compress(data, 9), n
 
 
 def _records(rng, lay, count):
@@ -59,7 +66,7 @@ def _records(rng, lay, count):
     return recs
 
 
-@pytest.mark.parametrize("shape,quality,count", [((48, 64), 7, 4), ((96, 160), 25, 3)])
+@pytest.mark.parametrize("shape,quality,count", [((48, 64), 7, 4), ((64, 96), 25, 3)])
 def test_kernel_on_shim_matches_python_packer(shape, quality, count):
     from cpu_sim import simlib
 
@@ -99,10 +106,40 @@ def test_device_packer_on_real_factors_and_public_api():
     assert compression.qmf_encode_batch(imgs, quality=7) == want
 
 
+def test_kernel_on_shim_two_blocks():
+    """A 16 512-byte luma column of noise: more than 16 383 symbols, so the kernel flushes a block in mid-parse."""
+    from cpu_sim import simlib
+
+    cfg, lay = compression.resolve_plan(1024, 1032, (1, 1, 1), None, "YCbCr", (0.5, 0.5), (8, 8), (-16, 15), 10)
+    assert lay.rows[0] == 16512
+    meta = compression._metadata(torch.uint8, "YCbCr", True, (-16, 15), (8, 8), lay)
+    recs = np.random.default_rng(9).integers(-16, 16, size=(1, lay.record_bytes)).astype(np.int8)
+    assert simlib.pack_device(recs, cfg, packing.dict_to_bytes(meta)) == [packing.pack_qmf_record(recs[0], lay, meta)]
+
+
 @pytest.mark.gpu
-def test_device_packer_refuses_long_columns():
-    cfg, lay = compression.resolve_plan(1365, 2048, None, 7, "YCbCr", (0.5, 0.5), (8, 8), (-16, 15), 10)
-    assert _cabi.lib().lrfb_qmf_pack_device_workspace(C.byref(cfg), 4) == -1
+def test_device_packer_long_columns_several_blocks():
+    """CLIC-sized planes (43 776-byte luma columns, 11 008-byte chroma columns): several deflate blocks per column,
+    matches limited to MAX_DIST; noise, smooth and real-factor records against the native host packer (zlib)."""
+    from oracle import qmf_port as port
+
+    H, W = 1365, 2048
+    cfg, lay = compression.resolve_plan(H, W, None, 7, "YCbCr", (0.5, 0.5), (8, 8), (-16, 15), 10)
+    assert lay.rows[0] == 43776
+    meta = compression._metadata(torch.uint8, "YCbCr", True, (-16, 15), (8, 8), lay)
+    recs = _records(np.random.default_rng(13), lay, 5)
+    img = port.s_nat(1000, H, W).unsqueeze(0)
+    real, _, _ = compression.qmf_encode_batch(img, quality=7, return_records=True)
+    recs[4] = real[0].cpu().numpy()
+    want = compression.pack_records(recs, cfg, lay, meta)
+    assert compression.pack_records_device(torch.from_numpy(recs).cuda(), cfg, lay, meta) == want
+    assert compression.qmf_encode_batch(img, quality=7) == [want[4]]
+
+
+@pytest.mark.gpu
+def test_device_packer_refuses_columns_beyond_the_window():
+    cfg, lay = compression.resolve_plan(2048, 2048, None, 7, "YCbCr", (0.5, 0.5), (8, 8), (-16, 15), 10)  # 65 536 rows
+    assert _cabi.lib().lrfb_qmf_pack_device_workspace(C.byref(cfg), 2) == -1
 
 
 @pytest.mark.gpu

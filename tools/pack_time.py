@@ -1,5 +1,5 @@
 """Dev tool: device time of the lossless stage (lrfb_qmf_pack_device) on real factor records of 768x512 images, its
-bytes against the host packer, and the host packer's time beside it:  python tools/pack_time.py [B] [distinct]"""
+bytes against the host packer, and the host packer's time beside it:  python tools/pack_time.py [B] [distinct] [H W]"""
 import ctypes as C
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -9,7 +9,7 @@ from lrf_b200 import _cabi, compression, packing
 from oracle import qmf_port as port
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 D = int(sys.argv[2]) if len(sys.argv) > 2 else 16
-H, W = 512, 768
+H, W = (int(sys.argv[3]), int(sys.argv[4])) if len(sys.argv) > 4 else (512, 768)
 pool = torch.stack([port.s_nat(1000 + i, H, W) for i in range(D)])
 imgs = pool[torch.arange(B) % D].cuda().contiguous()
 cfg, lay = compression.resolve_plan(H, W, None, 7, "YCbCr", (0.5, 0.5), (8, 8), (-16, 15), 10)
