@@ -503,6 +503,26 @@ def main():
                                       "quality 7, 10 sweeps; M = (43776, 11008, 11008)" % (Bc, cimgs.numel() / 1e9),
                           "roofline": {"bound": "fp32", "achieved": ctf, "peak": fp32_peak, "unit": "TFLOP/s",
                                        "frac": ctf / fp32_peak, "flop_per_pixel": cfl / (Hc * Wc)}}
+        # the lossless stage on those records (43 776-byte luma columns: several deflate blocks each)
+        cmeta = _packing.dict_to_bytes(compression._metadata(torch.uint8, "YCbCr", True, KW["bounds"], KW["patch_size"], clay))
+        cpws = int(lib.lrfb_qmf_pack_device_workspace(C.byref(ccfg), Bc))
+        if cpws > 0:
+            ccap = Bc * int(lib.lrfb_qmf_pack_bound(C.byref(ccfg), len(cmeta)))
+            c_ws = torch.empty(cpws, dtype=torch.uint8, device=dev)
+            c_blob = torch.empty(ccap, dtype=torch.uint8, device=dev)
+            c_offs = torch.empty(Bc + 1, dtype=torch.int64, device=dev)
+
+            def cpack():
+                _cabi.check(lib.lrfb_qmf_pack_device(C.byref(ccfg), Bc, C.c_void_p(cplan.factors.data_ptr()), cmeta, len(cmeta),
+                                                     C.c_void_p(c_blob.data_ptr()), ccap, C.c_void_p(c_offs.data_ptr()),
+                                                     C.c_void_p(c_ws.data_ptr()), cpws,
+                                                     C.c_void_p(torch.cuda.current_stream().cuda_stream)), "lrfb_qmf_pack_device")
+
+            barrier()
+            cpms = allmax(time_steps_ms(cpack, 2, 1))
+            extras["clic"]["pack"] = {"value": cmpix / (cpms / 1e3), "unit": "Mpixel/s", "ms_per_step": cpms,
+                                      "stream_bytes_out": int(c_offs[Bc].item()), "factor_bytes_in": int(cplan.factors.numel())}
+            del c_ws, c_blob, c_offs
         del cplan, cimgs
         torch.cuda.empty_cache()
 

@@ -13,7 +13,8 @@ lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "lrf_b200", "csrc
 OPS = [("UTC*MMA (tcgen05.mma)", r"\bUTC\w*MMA"), ("LDTM (tcgen05.ld)", r"\bLDTM"), ("STTM (tcgen05.st)", r"\bSTTM"),
        ("UTMALDG (TMA load)", r"\bUTMALDG"), ("SYNCS (mbarrier)", r"\bSYNCS"), ("FFMA2", r"\bFFMA2"), ("FFMA", r"\bFFMA\b"),
        ("DFMA", r"\bDFMA"), ("DMMA", r"\bDMMA"), ("IDP.4A", r"\bIDP\.4A"), ("LDGSTS (cp.async)", r"\bLDGSTS"),
-       ("UCGABAR (cluster barrier)", r"\bUCGABAR"), ("REDUX", r"\bREDUX")]
+       ("UCGABAR (cluster barrier)", r"\bUCGABAR"), ("C?REDUX", r"\bC?REDUX"), ("MATCH (match.any)", r"\bMATCH"),
+       ("VOTE (ballot)", r"\bVOTE"), ("ATOMS (shared atomics)", r"\bATOMS")]
 sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
 counts = collections.OrderedDict()
 cur = None
