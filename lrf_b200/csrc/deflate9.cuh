@@ -414,7 +414,10 @@ constexpr int kWarps = 4;             // warps per long column: warp 0 runs the 
 #define D9_LONG 2048
 #endif
 constexpr int kLongColumn = D9_LONG;     // columns above this many bytes get kWarps warps, the others one
-constexpr int kWide = 2;              // chain candidates per lane and step
+#ifndef D9_WIDE
+#define D9_WIDE 2
+#endif
+constexpr int kWide = D9_WIDE;              // chain candidates per lane and step
 constexpr int kStep = 32 * kWide;     // candidates per step of one warp
 constexpr int kParMin = 4 * kStep;    // chains with more candidates than this are walked by all warps of the CTA
 struct Task {
