@@ -80,11 +80,14 @@ def test_kernel_on_shim_matches_python_packer(shape, quality, count):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape,quality,batch", [((512, 768), 7, 24), ((96, 160), 25, 33), ((200, 328), 3, 7)])
-def test_device_packer_matches_python_packer(shape, quality, batch):
+@pytest.mark.parametrize("shape,quality,batch,space", [((512, 768), 7, 24, "YCbCr"), ((96, 160), 25, 33, "YCbCr"),
+                                                       ((200, 328), 3, 7, "YCbCr"), ((8, 8), 50, 3, "YCbCr"),
+                                                       ((16, 24), 100, 5, "YCbCr"), ((128, 192), 30, 6, "RGB")])
+def test_device_packer_matches_python_packer(shape, quality, batch, space):
+    """Ragged shapes down to one-row factor columns (1- and 2-byte streams), full-rank factors (64 columns), RGB planes."""
     H, W = shape
-    cfg, lay = compression.resolve_plan(H, W, None, quality, "YCbCr", (0.5, 0.5), (8, 8), (-16, 15), 10)
-    meta = compression._metadata(torch.uint8, "YCbCr", True, (-16, 15), (8, 8), lay)
+    cfg, lay = compression.resolve_plan(H, W, None, quality, space, (0.5, 0.5), (8, 8), (-16, 15), 10)
+    meta = compression._metadata(torch.uint8, space, True, (-16, 15), (8, 8), lay)
     recs = _records(np.random.default_rng(7), lay, batch)
     want = [packing.pack_qmf_record(recs[i], lay, meta) for i in range(batch)]
     got = compression.pack_records_device(torch.from_numpy(recs).cuda(), cfg, lay, meta)
