@@ -5,8 +5,10 @@
     E(matrix)           = combine(json{"num_fibers","mode","dtype"}, combine_bytes(zlib9 per column))  :354-390
     image               = combine(json(metadata), combine_bytes([E(U_y), E(V_y), ...]))  compression/qmf.py:288-290
 
-zlib stays on the host (north_star) and is timed separately; the device hands over factors already
-fiber-major, so each column is a contiguous slice and is compressed without a transpose.
+This module is the host form (north_star: lossless packing on the host, timed separately — bench.py `host_pack`); the
+device hands over factors already fiber-major, so each column is a contiguous slice and is compressed without a
+transpose.  The same bytes also come from the GPU: `lrfb_qmf_pack_device` (lrf_b200/csrc/deflate9.cuh, zlib level 9
+restated as a kernel; bench.py `pack`), which `compression.qmf_encode_batch` uses when the shape allows.
 """
 from __future__ import annotations
 
