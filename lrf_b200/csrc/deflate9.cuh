@@ -11,14 +11,16 @@
 // the zlib wrapper (78 DA ... adler32).  Parity anchor: the system zlib itself (tests/test_deflate9.py compares every
 // stream byte for byte).
 //
-// Mapping: one warp per column.  The hash chains zlib walks serially (prev[] links, newest first) become a
-// random-access structure: positions are radix-sorted by (hash, position), so the chain of position p is the run of
-// entries just below p's rank, and the 32 lanes test 32 chain candidates per step — quick reject on the two bytes
-// around the current best length, 4-byte compares, then "first lane that reaches nice_length stops the walk, otherwise
-// the closest of the longest" which is exactly what the serial walk with its strict > update returns.  The chain-length
-// budget (4096, a quarter of it once the previous match is >= 32 long) counts candidates the same way.  Lane 0 builds the
-// three Huffman trees (small: <= 286 leaves) and the tree header; the symbols are then coded by all lanes (prefix sum of
-// code lengths, OR into the staged output).
+// Mapping: one warp per column (four warps per long column when the batch has fewer long columns than single-warp slots).
+// The hash chains zlib walks serially (prev[] links, newest first) become a random-access structure: positions are
+// radix-sorted by (hash, position), so the chain of position p is the run of entries just below p's rank, and the lanes
+// test 64 chain candidates per step: a four-byte filter (the two bytes of zlib's own quick check around the current best
+// length plus two offsets that follow where the last survivors parted from the string at p), then the survivors are compared
+// in chain order by the whole warp, 128 bytes per round.  "The first candidate that reaches nice_length stops the walk,
+// otherwise the closest of the longest" is exactly what the serial walk with its strict > update returns.  The
+// chain-length budget (4096, a quarter of it once the previous match is >= 32 long) counts candidates the same way.  Lane 0
+// builds the three Huffman trees (small: <= 286 leaves) and the tree header; the symbols are then coded by all lanes
+// (prefix sum of code lengths, OR into the staged output).
 #pragma once
 #include "lrfb_common.cuh"
 
@@ -413,7 +415,7 @@ constexpr int kWarps = 4;             // warps per long column: warp 0 runs the 
 #ifndef D9_LONG
 #define D9_LONG 2048
 #endif
-constexpr int kLongColumn = D9_LONG;     // columns above this many bytes get kWarps warps, the others one
+constexpr int kLongColumn = D9_LONG;  // columns above this many bytes may get kWarps warps (small batches), the others one
 #ifndef D9_WIDE
 #define D9_WIDE 2
 #endif
