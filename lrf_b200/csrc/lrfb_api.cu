@@ -593,11 +593,11 @@ struct SideStream {
   cudaStream_t stream = nullptr, stream2 = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr, init2 = nullptr;
 };
-SideStream* side_stream() {  // returns with s->mu LOCKED (or nullptr)
-  static SideStream table[64];
+SideStream* side_stream(int which = 0) {  // returns with s->mu LOCKED (or nullptr); set 0: encode, set 1: lossless stage
+  static SideStream table[2][64];
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  SideStream& s = table[dev];
+  SideStream& s = table[which][dev];
   s.mu.lock();
   if (!s.ready && !s.failed) {
     // lowest priority: luma-chain blocks (caller's stream) are scheduled first, chroma fills what is left
@@ -1464,7 +1464,7 @@ struct PackPlan {
   int group_len[6];         // distinct column lengths, longest first
   int grid[6];
   bool wide[6];            // four warps per column (few long columns) or one
-  long long off_cbuf, off_csize, off_sizes, off_counter, off_scratch, total;
+  long long off_cbuf, off_csize, off_sizes, off_counter, off_scratch[6], total;  // one scratch region per launch: they overlap in time
 };
 int ctas_per_sm(int len, bool wide) {
   const int per = d9::smem_bytes(len) + 1024;  // 1 KB of system-reserved shared memory per CTA
@@ -1502,14 +1502,14 @@ int make_pack_plan(const lrfb_qmf_config* cfg, int batch, PackPlan& P) {
   if (so > 0x7fffffffll) return fail(LRFB_E_UNSUPPORTED, "image record too large");
   std::sort(P.group_len, P.group_len + P.n_groups, [](int a, int b) { return a > b; });
   P.img_stride = so;
-  long long scratch = 0;
+  long long scratch[6] = {0};
   for (int g = 0; g < P.n_groups; ++g) {
     long long streams = 0;
     for (int mtx = 0; mtx < P.n_mat; ++mtx)
       if (P.len[mtx] == P.group_len[g]) streams += (long long)batch * P.ncols[mtx];
     P.wide[g] = use_wide(P.group_len[g], streams);
     P.grid[g] = (int)std::min<long long>(streams, (long long)num_sms() * ctas_per_sm(P.group_len[g], P.wide[g]));
-    scratch = std::max(scratch, P.grid[g] * d9::scratch_per_cta(P.group_len[g]));
+    scratch[g] = P.grid[g] * d9::scratch_per_cta(P.group_len[g]);
   }
   auto up = [](long long v) { return (v + 255) & ~255ll; };
   long long o = 0;
@@ -1517,7 +1517,7 @@ int make_pack_plan(const lrfb_qmf_config* cfg, int batch, PackPlan& P) {
   P.off_csize = o, o = up(o + 4ll * batch * P.cols_total);
   P.off_sizes = o, o = up(o + 8ll * batch);
   P.off_counter = o, o = up(o + 64);
-  P.off_scratch = o, o = up(o + scratch);
+  for (int g = 0; g < P.n_groups; ++g) P.off_scratch[g] = o, o = up(o + scratch[g]);
   P.total = o;
   return 0;
 }
@@ -1543,7 +1543,22 @@ LRFB_EXPORT int32_t lrfb_qmf_pack_device(const lrfb_qmf_config* cfg, int32_t bat
   cudaStream_t st = (cudaStream_t)(uintptr_t)stream;
   unsigned char* ws = reinterpret_cast<unsigned char*>(d_workspace);
   if (cudaMemsetAsync(ws + P.off_counter, 0, 64, st) != cudaSuccess) return fail(LRFB_E_ARG, "memset failed");
+  // The launch of the longest columns (luma) goes to the caller's stream, the others to a low-priority helper stream:
+  // their CTAs move in as the long launch drains (its last wave is mostly empty), instead of waiting for its end.
+#ifndef LRFB_SIM
+  SideStream* side = P.n_groups > 1 ? side_stream(1) : nullptr;
+  SideUnlock side_guard{side};
+  if (side) {
+    cudaEventRecord(side->fork, st);
+    cudaStreamWaitEvent(side->stream, side->fork, 0);
+  }
+#endif
   for (int g = 0; g < P.n_groups; ++g) {
+#ifndef LRFB_SIM
+    cudaStream_t gs = (g > 0 && side) ? side->stream : st;
+#else
+    cudaStream_t gs = st;
+#endif
     d9::Params K;
     memset(&K, 0, sizeof(K));
     K.rec = reinterpret_cast<const unsigned char*>(d_records), K.rec_stride = P.L.record_bytes;
@@ -1557,7 +1572,7 @@ LRFB_EXPORT int32_t lrfb_qmf_pack_device(const lrfb_qmf_config* cfg, int32_t bat
     K.cols_total = P.cols_total, K.batch = batch;
     K.cbuf = ws + P.off_cbuf, K.img_stride = P.img_stride;
     K.csize = reinterpret_cast<unsigned*>(ws + P.off_csize);
-    K.scratch = ws + P.off_scratch;
+    K.scratch = ws + P.off_scratch[g];
     K.counter = reinterpret_cast<int*>(ws + P.off_counter) + g;
     const int smem = d9::smem_bytes(K.len);
     const bool wide = P.wide[g], multi = K.len > d9::kOneBlock;
@@ -1571,9 +1586,15 @@ LRFB_EXPORT int32_t lrfb_qmf_pack_device(const lrfb_qmf_config* cfg, int32_t bat
     }
     cudaFuncSetAttribute((const void*)fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 #endif
-    LRFB_LAUNCH(fn, dim3(P.grid[g]), dim3(wide ? 32 * d9::kWarps : 32), smem, st, K);
+    LRFB_LAUNCH(fn, dim3(P.grid[g]), dim3(wide ? 32 * d9::kWarps : 32), smem, gs, K);
     if ((rc = check_launch("deflate9_kernel"))) return rc;
   }
+#ifndef LRFB_SIM
+  if (side) {
+    cudaEventRecord(side->join, side->stream);
+    cudaStreamWaitEvent(st, side->join, 0);
+  }
+#endif
   d9::FrameParams F;
   memset(&F, 0, sizeof(F));
   F.n_mat = P.n_mat;
