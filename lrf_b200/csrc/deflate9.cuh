@@ -650,8 +650,10 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 32 : 8) deflate9_kernel(Par
       }
       continue;
     }
-    const int img = s / P.cols_per_image;
-    int j = s - img * P.cols_per_image, sg = 0;
+    // hand out the columns of high rank index first: they carry less signal (long zero runs, long hash chains) and take
+    // several times longer than the leading columns, which then fill the tail of the launch
+    const int img = s % P.batch;
+    int j = P.cols_per_image - 1 - s / P.batch, sg = 0;
     while (sg + 1 < P.n_seg && j >= P.seg[sg].ncols) j -= P.seg[sg].ncols, ++sg;
     const unsigned char* src = P.rec + (long long)img * P.rec_stride + P.seg[sg].rec_off + (long long)j * n;
     unsigned char* dst = P.cbuf + (long long)img * P.img_stride + P.seg[sg].out_off + (long long)j * P.slot;
