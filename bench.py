@@ -202,7 +202,7 @@ def main():
     ap.add_argument("--clic-batch", type=int, default=256, help="2048x1365 images per GPU for the clic leg")
     ap.add_argument("--side-batch", type=int, default=1024, help="images for the ablation leg")
     ap.add_argument("--svd-batch", type=int, default=4096, help="images for the svd leg (configs[2] names the 4096 batch)")
-    ap.add_argument("--bytes-images", type=int, default=1024, help="images per GPU for e2e_bytes")
+    ap.add_argument("--bytes-images", type=int, default=4096, help="images per GPU for e2e_bytes")
     ap.add_argument("--parity-images", type=int, default=32, help="images compared with the oracle port")
     args = ap.parse_args()
 

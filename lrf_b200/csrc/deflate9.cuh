@@ -412,6 +412,7 @@ __device__ unsigned long long g_d9_prof[16];
 #define D9_C(i, v)
 #endif
 constexpr int kWarps = 4;             // warps per long column: warp 0 runs the serial parts, every warp walks its share of long chains
+constexpr int kWarpsHuge = 8;         // ... and per column so long that shared memory holds one or two of them per SM
 #ifndef D9_LONG
 #define D9_LONG 2048
 #endif
@@ -612,7 +613,7 @@ __device__ __noinline__ void flush_block_out(BlockOut& b, int end, int last, int
 // NW warps per column: 4 shorten a long column's critical path (shared chain walks), 1 puts more columns on an SM.
 // MULTI: columns above kOneBlock bytes (several deflate blocks, flushed in mid-parse).
 template <int NW, bool MULTI>
-__global__ void __launch_bounds__(32 * NW, NW == 1 ? 32 : 8) deflate9_kernel(Params P) {
+__global__ void __launch_bounds__(32 * NW, NW == 1 ? 32 : NW <= 4 ? 8 : 2) deflate9_kernel(Params P) {
   LRFB_DYN_SMEM(smem);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = P.len, m = n >= 3 ? n - 2 : 0, lp = pad_len(n);

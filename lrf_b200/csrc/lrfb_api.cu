@@ -1463,20 +1463,23 @@ struct PackPlan {
   int n_groups;
   int group_len[6];         // distinct column lengths, longest first
   int grid[6];
-  bool wide[6];            // four warps per column (few long columns) or one
+  int nw[6];               // warps per column: 1, kWarps (few long columns) or kWarpsHuge (shared memory holds < 4 per SM)
   long long off_cbuf, off_csize, off_sizes, off_counter, off_scratch[6], total;  // one scratch region per launch: they overlap in time
 };
-int ctas_per_sm(int len, bool wide) {
+int ctas_per_sm(int len, int nw) {
   const int per = d9::smem_bytes(len) + 1024;  // 1 KB of system-reserved shared memory per CTA
-  // the kernel's __launch_bounds__: 8 CTAs of kWarps warps, or 32 single-warp CTAs
-  return std::max(1, std::min(wide ? 8 : 32, (227 * 1024) / per));
+  // the kernel's __launch_bounds__: 32 single-warp CTAs, 8 of kWarps warps, 2 of kWarpsHuge
+  return std::max(1, std::min(nw == 1 ? 32 : nw <= d9::kWarps ? 8 : 2, (227 * 1024) / per));
 }
 // One warp per column gives the most columns in flight and the best throughput (measured on 4096 images of 768x512:
 // 39.7 ms against 51.8 ms with four warps per luma column).  Four warps per column shorten a column's critical path
 // (the long chain walks are shared), which is what counts when there are fewer long columns than single-warp slots:
-// one image, small batches.
-bool use_wide(int len, long long streams) {
-  return len > d9::kLongColumn && streams <= (long long)num_sms() * ctas_per_sm(len, false);
+// one image, small batches.  Columns so long that shared memory holds fewer than four per SM (CLIC-sized luma columns:
+// one) get eight warps: 256 CLIC-sized records 196 ms with one warp, 108 ms with four.
+int warps_per_column(int len, long long streams) {
+  if (len <= d9::kLongColumn) return 1;
+  if (ctas_per_sm(len, 1) < 4) return d9::kWarpsHuge;
+  return streams <= (long long)num_sms() * ctas_per_sm(len, 1) ? d9::kWarps : 1;
 }
 int make_pack_plan(const lrfb_qmf_config* cfg, int batch, PackPlan& P) {
   int rc = lrfb_qmf_layout_query(cfg, &P.L);
@@ -1507,8 +1510,8 @@ int make_pack_plan(const lrfb_qmf_config* cfg, int batch, PackPlan& P) {
     long long streams = 0;
     for (int mtx = 0; mtx < P.n_mat; ++mtx)
       if (P.len[mtx] == P.group_len[g]) streams += (long long)batch * P.ncols[mtx];
-    P.wide[g] = use_wide(P.group_len[g], streams);
-    P.grid[g] = (int)std::min<long long>(streams, (long long)num_sms() * ctas_per_sm(P.group_len[g], P.wide[g]));
+    P.nw[g] = warps_per_column(P.group_len[g], streams);
+    P.grid[g] = (int)std::min<long long>(streams, (long long)num_sms() * ctas_per_sm(P.group_len[g], P.nw[g]));
     scratch[g] = P.grid[g] * d9::scratch_per_cta(P.group_len[g]);
   }
   auto up = [](long long v) { return (v + 255) & ~255ll; };
@@ -1575,10 +1578,12 @@ LRFB_EXPORT int32_t lrfb_qmf_pack_device(const lrfb_qmf_config* cfg, int32_t bat
     K.scratch = ws + P.off_scratch[g];
     K.counter = reinterpret_cast<int*>(ws + P.off_counter) + g;
     const int smem = d9::smem_bytes(K.len);
-    const bool wide = P.wide[g], multi = K.len > d9::kOneBlock;
+    const int nw = P.nw[g];
+    const bool multi = K.len > d9::kOneBlock;
     typedef void (*kernel_t)(d9::Params);
-    const kernel_t fn = wide ? (multi ? d9::deflate9_kernel<d9::kWarps, true> : d9::deflate9_kernel<d9::kWarps, false>)
-                             : (multi ? d9::deflate9_kernel<1, true> : d9::deflate9_kernel<1, false>);
+    const kernel_t fn = nw == d9::kWarpsHuge ? (multi ? d9::deflate9_kernel<d9::kWarpsHuge, true> : d9::deflate9_kernel<d9::kWarpsHuge, false>)
+                        : nw == d9::kWarps   ? (multi ? d9::deflate9_kernel<d9::kWarps, true> : d9::deflate9_kernel<d9::kWarps, false>)
+                                             : (multi ? d9::deflate9_kernel<1, true> : d9::deflate9_kernel<1, false>);
 #ifndef LRFB_SIM
     if (smem > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -1586,7 +1591,7 @@ LRFB_EXPORT int32_t lrfb_qmf_pack_device(const lrfb_qmf_config* cfg, int32_t bat
     }
     cudaFuncSetAttribute((const void*)fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 #endif
-    LRFB_LAUNCH(fn, dim3(P.grid[g]), dim3(wide ? 32 * d9::kWarps : 32), smem, gs, K);
+    LRFB_LAUNCH(fn, dim3(P.grid[g]), dim3(32 * nw), smem, gs, K);
     if ((rc = check_launch("deflate9_kernel"))) return rc;
   }
 #ifndef LRFB_SIM
