@@ -462,7 +462,11 @@ def main():
                       "workload": "lrfb_qmf_pack_device on the %d records per GPU of the encode above: zlib level 9 per factor "
                                   "column (one warp each) + framing, byte-identical to the host packer" % B,
                       "factor_bytes_in": int(plan.factors.numel()), "stream_bytes_out": int(d_offs[B].item()),
-                      "vs_host_packer": (mpix_step / world / (pms / 1e3)) / (n_s * H * W / 1e6 / pack_s)}
+                      "vs_host_packer": (mpix_step / world / (pms / 1e3)) / (n_s * H * W / 1e6 / pack_s),
+                      "roofline": {"bound": "issue", "what": "integer / shared-memory latency work: ncu (profiles/r2_full_deflate9_b4096.txt) "
+                                   "shows 40 % of the SM issue rate with 11 columns (warps) per SM and DRAM at 0.1 %; the HBM fraction of "
+                                   "the algorithmic bytes (factors in + streams out) is given to show it is not the bound",
+                                   "hbm_frac": (int(plan.factors.numel()) + int(d_offs[B].item())) / (pms / 1e3) / 1e9 / peaks["hbm_gbs"]}}
     del d_pws, d_blob, d_offs
 
     # ---- end to end to `bytes` through the Python API: pinned host uint8 images -> list[bytes] -------------------------
