@@ -201,6 +201,15 @@ int32_t lrfb_qmf_pack_device(const lrfb_qmf_config* cfg, int32_t batch, const in
                              const char* metadata_json, int64_t metadata_len, uint8_t* d_blob, int64_t blob_capacity,
                              int64_t* d_offsets, void* d_workspace, int64_t workspace_bytes, void* stream);
 
+/* The inverse on the device — the head of lrf.qmf_decode (lrf/compression/qmf.py:313-327: separate_bytes, decode_tensor ->
+ * zlib.decompress per column, lrf/compression/utils.py:393-426, :458-490): un-frames `batch` encoded images of one shape
+ * (d_blob[d_offsets[i] .. d_offsets[i+1]), device memory) and inflates every factor column into the int8 records
+ * lrfb_qmf_decode reads.  Accepts any valid zlib stream (reference, host packer, device packer).  Synchronises the
+ * stream and returns LRFB_E_ARG naming the first malformed image (framing, deflate data, column length, adler32). */
+int64_t lrfb_qmf_unpack_device_workspace(const lrfb_qmf_config* cfg, int32_t batch);
+int32_t lrfb_qmf_unpack_device(const lrfb_qmf_config* cfg, int32_t batch, const uint8_t* d_blob, const int64_t* d_offsets,
+                               int8_t* d_records, void* d_workspace, int64_t workspace_bytes, void* stream);
+
 /* The whole of lrf.qmf_encode for a batch with HOST buffers (lrf/compression/qmf.py:116-292): images in, finished byte
  * streams out.  The chunked pipeline of lrfb_qmf_encode_host with lrfb_qmf_pack_device behind every chunk; only the
  * compressed streams cross PCIe on the way back.  Image i's stream is h_blob[h_offsets[i] .. h_offsets[i+1]);

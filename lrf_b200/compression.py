@@ -128,6 +128,32 @@ def encode_bytes_host(images: torch.Tensor, cfg, lay, meta: dict, device_index: 
     return [bytes(mv[o[i] : o[i + 1]]) for i in range(B)]
 
 
+DEVICE_UNPACK = False  # qmf_decode_batch un-frames and inflates on the device (lrfb_qmf_unpack_device) instead of per image on the host
+
+
+def unpack_records_device(encoded: list[bytes], cfg, lay, device) -> torch.Tensor:
+    """B encoded streams of one shape -> int8 factor records (B, record_bytes) on the device: the framing is walked and
+    every zlib stream inflated by ``lrfb_qmf_unpack_device`` (lrf_b200/csrc/inflate9.cuh); only the streams cross PCIe.
+    Raises LrfbError naming the first malformed image."""
+    B = len(encoded)
+    sizes = np.fromiter((len(e) for e in encoded), np.int64, B)
+    offs = np.zeros(B + 1, np.int64)
+    np.cumsum(sizes, out=offs[1:])
+    blob = torch.frombuffer(bytearray(b"".join(encoded)), dtype=torch.uint8)
+    lib = _cabi.lib()
+    wsb = int(lib.lrfb_qmf_unpack_device_workspace(C.byref(cfg), B))
+    if wsb <= 0:
+        raise _cabi.LrfbError("lrfb_qmf_unpack_device_workspace failed")
+    d_blob = blob.to(device)
+    d_offs = torch.from_numpy(offs).to(device)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=device)
+    rec = torch.empty((B, lay.record_bytes), dtype=torch.int8, device=device)
+    rc = lib.lrfb_qmf_unpack_device(C.byref(cfg), B, C.c_void_p(d_blob.data_ptr()), C.c_void_p(d_offs.data_ptr()),
+                                    C.c_void_p(rec.data_ptr()), C.c_void_p(ws.data_ptr()), wsb, _stream_ptr())
+    _cabi.check(rc, "lrfb_qmf_unpack_device")
+    return rec
+
+
 def _require_cuda() -> None:
     if not torch.cuda.is_available():
         raise _cabi.LrfbError("lrf_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
@@ -435,8 +461,12 @@ def qmf_decode_batch(encoded: list[bytes], device=None) -> torch.Tensor:
         if metas[0]["dtype"] != "uint8":
             raise NotImplementedError("lrf_b200: only uint8 images are decoded on the CUDA path")
         return _qmf_decode_nopatch(metas, [h[1] for h in heads], device)
+    cfg, lay = _decode_config(metas[0])
+    head = encoded[0][: 4 + len(heads[0][0])]
+    if DEVICE_UNPACK and all(e[: len(head)] == head for e in encoded):  # one shape, one header: un-frame + inflate on the device
+        with torch.cuda.device(device):
+            return decode_records(unpack_records_device(encoded, cfg, lay, device), cfg)
     parsed = list(_pool().map(_parse_encoded, encoded))
-    cfg, lay = _decode_config(parsed[0][0])
     host = np.empty((len(encoded), lay.record_bytes), np.int8)
     for i, (_, fibers) in enumerate(parsed):
         for pl in range(lay.n_planes):

@@ -21,6 +21,7 @@
 #include "bcd_tc.cuh"
 #include "decode.cuh"
 #include "deflate9.cuh"
+#include "inflate9.cuh"
 #include "eig.cuh"
 #include "frontend.cuh"
 #include "frontgram.cuh"
@@ -1743,6 +1744,68 @@ LRFB_EXPORT int32_t lrfb_qmf_encode_bytes_host(lrfb_ctx* c, const lrfb_qmf_confi
   if ((rc = sync_stream(c->pack[1]))) return rc;
 #endif
   return sync_stream(c->stream);
+}
+
+// ---- the inverse on the device: un-frame + inflate a batch of encoded images into int8 records ---------------------------
+LRFB_EXPORT int64_t lrfb_qmf_unpack_device_workspace(const lrfb_qmf_config* cfg, int32_t batch) {
+  lrfb_qmf_layout L;
+  if (batch <= 0 || lrfb_qmf_layout_query(cfg, &L)) return -1;
+  int cols_total = 0;
+  for (int pl = 0; pl < L.n_planes; ++pl) cols_total += 2 * L.rank[pl];
+  return 256 + 8ll * batch * cols_total;
+}
+
+LRFB_EXPORT int32_t lrfb_qmf_unpack_device(const lrfb_qmf_config* cfg, int32_t batch, const uint8_t* d_blob,
+                                           const int64_t* d_offsets, int8_t* d_records, void* d_workspace,
+                                           int64_t workspace_bytes, void* stream) {
+  if (!d_blob || !d_offsets || !d_records || !d_workspace || batch <= 0) return fail(LRFB_E_ARG, "bad arguments");
+  lrfb_qmf_layout L;
+  int rc = lrfb_qmf_layout_query(cfg, &L);
+  if (rc) return rc;
+  d9i::Params P;
+  memset(&P, 0, sizeof(P));
+  P.blob = d_blob, P.offsets = reinterpret_cast<const long long*>(d_offsets), P.batch = batch;
+  P.n_mat = 2 * L.n_planes;
+  for (int mtx = 0; mtx < P.n_mat; ++mtx) {
+    const int pl = mtx >> 1;
+    P.ncols[mtx] = L.rank[pl], P.len[mtx] = (mtx & 1) ? L.cols : L.rows[pl];
+    P.rec_off[mtx] = (mtx & 1) ? L.v_offset[pl] : L.u_offset[pl];
+    P.col0[mtx] = P.cols_total, P.cols_total += P.ncols[mtx];
+    P.max_len = std::max(P.max_len, P.len[mtx]);
+  }
+  const int smem = d9i::smem_bytes(P.max_len);
+  if (smem > 227 * 1024) return fail(LRFB_E_UNSUPPORTED, "column of %d bytes does not fit the device inflate", P.max_len);
+  if (workspace_bytes < 256 + 8ll * batch * P.cols_total) return fail(LRFB_E_WORKSPACE, "workspace too small");
+  cudaStream_t st = (cudaStream_t)(uintptr_t)stream;
+  unsigned char* ws = reinterpret_cast<unsigned char*>(d_workspace);
+  P.error = reinterpret_cast<int*>(ws);
+  P.col_pos = reinterpret_cast<unsigned*>(ws + 256);
+  P.col_len = P.col_pos + (size_t)batch * P.cols_total;
+  P.rec = d_records, P.rec_stride = L.record_bytes;
+  if (cudaMemsetAsync(ws, 0, 256, st) != cudaSuccess) return fail(LRFB_E_ARG, "memset failed");
+  LRFB_LAUNCH(d9i::unframe_kernel, dim3((batch + 127) / 128), dim3(128), 0, st, P);
+  if ((rc = check_launch("unframe_kernel"))) return rc;
+#ifndef LRFB_SIM
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(d9i::inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return fail((int)e, "inflate shared memory %d: %s", smem, cudaGetErrorString(e));
+  }
+#endif
+  const long long streams = (long long)batch * P.cols_total;
+  const int per_sm = std::max(1, std::min(32, (227 * 1024) / (smem + 1024)));
+  const int grid = (int)std::min<long long>(streams, (long long)num_sms() * per_sm);
+  LRFB_LAUNCH(d9i::inflate_kernel, dim3(grid), dim3(32), smem, st, P);
+  if ((rc = check_launch("inflate_kernel"))) return rc;
+  int err = 0;
+#ifndef LRFB_SIM
+  cudaError_t e = cudaMemcpyAsync(&err, P.error, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return fail((int)e, "lrfb_qmf_unpack_device: %s", cudaGetErrorString(e));
+#else
+  err = *P.error;
+#endif
+  if (err) return fail(LRFB_E_ARG, "encoded image %d is malformed (framing, deflate stream, length or adler32)", err - 1);
+  return 0;
 }
 
 #ifdef D9_PROF

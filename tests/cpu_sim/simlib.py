@@ -183,3 +183,18 @@ def deflate9_serial(data: bytes) -> bytes:
     out = np.zeros(len(data) + 64, np.uint8)
     n = fn(data, len(data), _ptr(out))
     return out[:n].tobytes()
+
+
+def unpack_device(encoded, cfg):
+    """lrfb_qmf_unpack_device on the shim: list of encoded streams -> (B, record_bytes) int8 records."""
+    B = len(encoded)
+    L = layout(cfg)
+    offs = np.zeros(B + 1, np.int64)
+    np.cumsum([len(e) for e in encoded], out=offs[1:])
+    blob = np.frombuffer(b"".join(encoded), np.uint8).copy()
+    wsb = lib().lrfb_qmf_unpack_device_workspace(C.byref(cfg), B)
+    ws = np.zeros(wsb + 256, np.uint8)
+    rec = np.zeros((B, L.record_bytes), np.int8)
+    rc = lib().lrfb_qmf_unpack_device(C.byref(cfg), B, _ptr(blob), _ptr(offs), _ptr(rec), _ptr(ws), wsb, None)
+    _cabi.check(rc, "unpack_device", lib())
+    return rec
