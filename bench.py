@@ -467,7 +467,23 @@ def main():
                                    "shows 40 % of the SM issue rate with 11 columns (warps) per SM and DRAM at 0.1 %; the HBM fraction of "
                                    "the algorithmic bytes (factors in + streams out) is given to show it is not the bound",
                                    "hbm_frac": (int(plan.factors.numel()) + int(d_offs[B].item())) / (pms / 1e3) / 1e9 / peaks["hbm_gbs"]}}
-    del d_pws, d_blob, d_offs
+    # ---- and back: un-frame + inflate those streams into records on the device (the head of qmf_decode) ----------------
+    uws = int(lib.lrfb_qmf_unpack_device_workspace(C.byref(cfg), B))
+    d_uws = torch.empty(uws, dtype=torch.uint8, device=dev)
+    d_rec2 = torch.empty_like(plan.factors)
+
+    def unpack_only():
+        _cabi.check(lib.lrfb_qmf_unpack_device(C.byref(cfg), B, C.c_void_p(d_blob.data_ptr()), C.c_void_p(d_offs.data_ptr()),
+                                               C.c_void_p(d_rec2.data_ptr()), C.c_void_p(d_uws.data_ptr()), uws,
+                                               C.c_void_p(torch.cuda.current_stream().cuda_stream)), "lrfb_qmf_unpack_device")
+
+    barrier()
+    ums = allmax(time_steps_ms(unpack_only, 2, 1))
+    extras["unpack"] = {"value": mpix_step / (ums / 1e3), "unit": "Mpixel/s", "ms_per_step": ums,
+                        "workload": "lrfb_qmf_unpack_device on the %d streams per GPU written above: framing walked, every column "
+                                    "inflated (one warp each), adler32 checked" % B,
+                        "records_equal": bool(torch.equal(d_rec2, plan.factors))}
+    del d_pws, d_blob, d_offs, d_uws, d_rec2
 
     # ---- end to end to `bytes` through the Python API: pinned host uint8 images -> list[bytes] -------------------------
     if not args.quick:

@@ -128,7 +128,7 @@ def encode_bytes_host(images: torch.Tensor, cfg, lay, meta: dict, device_index: 
     return [bytes(mv[o[i] : o[i + 1]]) for i in range(B)]
 
 
-DEVICE_UNPACK = False  # qmf_decode_batch un-frames and inflates on the device (lrfb_qmf_unpack_device) instead of per image on the host
+DEVICE_UNPACK = True  # qmf_decode_batch un-frames and inflates on the device (lrfb_qmf_unpack_device) instead of per image on the host
 
 
 def unpack_records_device(encoded: list[bytes], cfg, lay, device) -> torch.Tensor:
