@@ -146,11 +146,17 @@ __device__ inline int build(Huff& h, const unsigned char* length, int n) {  // r
   return left;
 }
 __device__ inline int decode_sym(Bits& b, const Huff& h) {
+  if (b.cnt < 15) b.fill();  // a code is at most 15 bits: walk them in the buffer, consume what was used
+  unsigned long long bits = b.buf;
   int code = 0, first = 0, index = 0;
   for (int l = 1; l < 16; ++l) {
-    code |= (int)b.get(1);
+    code |= (int)(bits & 1ull);
+    bits >>= 1;
     const int count = h.count[l];
-    if (code - count < first) return h.symbol[index + (code - first)];
+    if (code - count < first) {
+      b.buf = bits, b.cnt -= l;
+      return h.symbol[index + (code - first)];
+    }
     index += count, first += count;
     first <<= 1, code <<= 1;
   }
