@@ -219,6 +219,13 @@ int32_t lrfb_qmf_encode_bytes_host(lrfb_ctx* ctx, const lrfb_qmf_config* cfg, in
                                    const char* metadata_json, int64_t metadata_len, uint8_t* h_blob,
                                    int64_t blob_capacity, int64_t* h_offsets);
 
+/* The whole of lrf.qmf_decode for a batch with HOST buffers (lrf/compression/qmf.py:295-353): encoded images in
+ * (h_blob[h_offsets[i] .. h_offsets[i+1]), h_offsets[0] = 0, one shape), uint8 images out ([batch][3][H][W]).
+ * lrfb_qmf_unpack_device + lrfb_qmf_decode with the copy-back of the images chunked behind the kernels; h_images should be
+ * pinned.  Returns LRFB_E_ARG naming the first malformed image. */
+int32_t lrfb_qmf_decode_bytes_host(lrfb_ctx* ctx, const lrfb_qmf_config* cfg, int32_t batch, const uint8_t* h_blob,
+                                   const int64_t* h_offsets, uint8_t* h_images);
+
 /* Test hook: select a kernel variant process-wide.  Knobs: "decode_v1" (1 = per-row float decoder instead of the
  * int8 dot-product one).  The shipped library reads no environment variables. */
 int32_t lrfb_debug_set(const char* knob, int32_t value);

@@ -94,6 +94,7 @@ PROTOTYPES = {
     "lrfb_qmf_unpack_device_workspace": (C.c_int64, [C.POINTER(QmfConfig), C.c_int32]),
     "lrfb_qmf_unpack_device": (C.c_int32, [C.POINTER(QmfConfig), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_int64, C.c_void_p]),
+    "lrfb_qmf_decode_bytes_host": (C.c_int32, [C.c_void_p, C.POINTER(QmfConfig), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "lrfb_debug_set": (C.c_int32, [C.c_char_p, C.c_int32]),
     "lrfb_qmf_decode_planes": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32),
                                            C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p,

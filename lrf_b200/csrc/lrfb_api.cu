@@ -1808,6 +1808,60 @@ LRFB_EXPORT int32_t lrfb_qmf_unpack_device(const lrfb_qmf_config* cfg, int32_t b
   return 0;
 }
 
+// Encoded images in host memory -> uint8 images in host memory, the whole of lrf.qmf_decode for a batch: the streams go up
+// once (a few KB per image), are un-framed and inflated on the device, and the decode kernel's output comes back chunk by
+// chunk behind the next chunk's kernel.
+LRFB_EXPORT int32_t lrfb_qmf_decode_bytes_host(lrfb_ctx* c, const lrfb_qmf_config* cfg, int32_t batch, const uint8_t* h_blob,
+                                               const int64_t* h_offsets, uint8_t* h_images) {
+  if (!c || !h_blob || !h_offsets || !h_images || batch <= 0) return fail(LRFB_E_ARG, "bad arguments");
+  lrfb_qmf_layout L;
+  int rc;
+  if ((rc = lrfb_qmf_layout_query(cfg, &L))) return rc;
+  const int64_t total = h_offsets[batch] - h_offsets[0];
+  if (h_offsets[0] != 0 || total <= 0) return fail(LRFB_E_ARG, "offsets must start at 0 and increase");
+  const int64_t uws = lrfb_qmf_unpack_device_workspace(cfg, batch);
+  if (uws <= 0) return fail(LRFB_E_UNSUPPORTED, "unsupported shape");
+#ifndef LRFB_SIM
+  cudaSetDevice(c->device);
+#endif
+  const size_t img_bytes = (size_t)3 * cfg->height * cfg->width;
+  const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)batch, c->chunk_bytes / std::max<size_t>(img_bytes, 1)));
+  if ((rc = grow(&c->d_in, &c->in_cap, (size_t)batch * L.record_bytes))) return rc;
+  if ((rc = grow(&c->d_out, &c->out_cap, (size_t)2 * chunk * img_bytes))) return rc;
+  if ((rc = grow(&c->d_blob, &c->blob_cap, (size_t)total + 256))) return rc;
+  if ((rc = grow(&c->d_offs, &c->offs_cap, (size_t)(batch + 1) * 8))) return rc;
+  if ((rc = grow(&c->d_pws, &c->pws_cap, (size_t)uws))) return rc;
+  if ((rc = h2d(c->d_blob, h_blob, (size_t)total, c->stream))) return rc;
+  if ((rc = h2d(c->d_offs, h_offsets, (size_t)(batch + 1) * 8, c->stream))) return rc;
+  if ((rc = lrfb_qmf_unpack_device(cfg, batch, reinterpret_cast<const uint8_t*>(c->d_blob), reinterpret_cast<const int64_t*>(c->d_offs),
+                                   reinterpret_cast<int8_t*>(c->d_in), c->d_pws, (int64_t)c->pws_cap, (void*)(uintptr_t)c->stream)))
+    return rc;
+  int idx = 0;
+  for (int i0 = 0; i0 < batch; i0 += chunk, ++idx) {
+    const int n = std::min(chunk, batch - i0);
+    const int oslot = idx & 1;
+    uint8_t* d_img = reinterpret_cast<uint8_t*>(c->d_out) + (size_t)oslot * chunk * img_bytes;
+#ifndef LRFB_SIM
+    if (idx >= 2) cudaStreamWaitEvent(c->stream, c->drained[oslot], 0);
+#endif
+    if ((rc = lrfb_qmf_decode(cfg, n, reinterpret_cast<const int8_t*>(c->d_in) + (size_t)i0 * L.record_bytes, d_img,
+                              (void*)(uintptr_t)c->stream)))
+      return rc;
+#ifndef LRFB_SIM
+    cudaEventRecord(c->encoded[oslot], c->stream);
+    cudaStreamWaitEvent(c->back, c->encoded[oslot], 0);
+    if ((rc = d2h(h_images + (size_t)i0 * img_bytes, d_img, (size_t)n * img_bytes, c->back))) return rc;
+    cudaEventRecord(c->drained[oslot], c->back);
+#else
+    if ((rc = d2h(h_images + (size_t)i0 * img_bytes, d_img, (size_t)n * img_bytes, c->stream))) return rc;
+#endif
+  }
+#ifndef LRFB_SIM
+  if ((rc = sync_stream(c->back))) return rc;
+#endif
+  return sync_stream(c->stream);
+}
+
 #ifdef D9_PROF
 LRFB_EXPORT int32_t lrfb_d9_prof(unsigned long long* out16, int32_t reset) {
   if (out16) cudaMemcpyFromSymbol(out16, d9::g_d9_prof, sizeof(unsigned long long) * 16);

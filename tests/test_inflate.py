@@ -67,3 +67,38 @@ def test_decode_batch_takes_the_device_route_and_matches_the_oracle():
             compression.qmf_decode_batch(blobs[:2] + [bytes(bad)] + blobs[3:])
     finally:
         compression.DEVICE_UNPACK = keep
+
+
+@pytest.mark.gpu
+def test_decode_bytes_host_matches_decode_batch():
+    """lrfb_qmf_decode_bytes_host (encoded images in host memory -> pinned uint8 images, chunked copy-back) equals the
+    device route of qmf_decode_batch; 37 images over 5 chunks with a ragged tail."""
+    from oracle import qmf_port as port
+
+    H, W, B = 96, 160, 37
+    pool = torch.stack([port.s_nat(2000 + i, H, W) for i in range(5)])
+    imgs = pool[torch.arange(B) % 5].contiguous()
+    blobs = compression.qmf_encode_batch(imgs, quality=12)
+    want = compression.qmf_decode_batch(blobs).cpu()
+    cfg, lay = compression._decode_config(packing.bytes_to_dict(packing.separate_bytes(blobs[0], 2)[0]))
+    offs = np.zeros(B + 1, np.int64)
+    np.cumsum([len(b) for b in blobs], out=offs[1:])
+    blob = np.frombuffer(b"".join(blobs), np.uint8).copy()
+    out = torch.empty((B, 3, H, W), dtype=torch.uint8, pin_memory=True)
+    lib = _cabi.lib()
+    ctx = C.c_void_p()
+    _cabi.check(lib.lrfb_ctx_create(0, C.byref(ctx)), "ctx")
+    try:
+        _cabi.check(lib.lrfb_ctx_set_chunk_bytes(ctx, 8 * 3 * H * W), "chunk")
+        for _ in range(2):
+            out.zero_()
+            rc = lib.lrfb_qmf_decode_bytes_host(ctx, C.byref(cfg), B, blob.ctypes.data_as(C.c_void_p),
+                                                offs.ctypes.data_as(C.c_void_p), C.c_void_p(out.data_ptr()))
+            _cabi.check(rc, "lrfb_qmf_decode_bytes_host")
+            assert torch.equal(out, want)
+        blob[int(offs[4]) - 9] ^= 0x10  # inside the last column stream of image 3
+        rc = lib.lrfb_qmf_decode_bytes_host(ctx, C.byref(cfg), B, blob.ctypes.data_as(C.c_void_p),
+                                            offs.ctypes.data_as(C.c_void_p), C.c_void_p(out.data_ptr()))
+        assert rc != 0 and b"image 3" in lib.lrfb_last_error()
+    finally:
+        lib.lrfb_ctx_destroy(ctx)
