@@ -324,6 +324,27 @@ def main():
         dist.all_reduce(tb, op=dist.ReduceOp.MAX)
     e2e_bytes_value = mpix_step / float(tb.item())
     e2e_blob_bytes = int(h_offs[B].item())
+
+    # ---- and the way back with host buffers (N = 1 only: one more pinned image buffer): encoded images -> uint8 images ---
+    decode_e2e = None
+    if world == 1 and not args.quick:
+        h_dec = torch.empty((B, 3, H, W), dtype=torch.uint8, pin_memory=True)
+
+        def dec_bytes_step():
+            _cabi.check(lib.lrfb_qmf_decode_bytes_host(ctx, C.byref(cfg), B, C.c_void_p(h_blob.data_ptr()), C.c_void_p(h_offs.data_ptr()),
+                                                       C.c_void_p(h_dec.data_ptr())), "lrfb_qmf_decode_bytes_host")
+
+        dec_bytes_step()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            dec_bytes_step()
+        tdb = (time.perf_counter() - t0) / args.e2e_steps
+        ref_dec = compression.decode_records(plan.factors[:8], cfg).cpu()
+        decode_e2e = {"value": mpix_step / tdb, "unit": "Mpixel/s", "h2d_bytes_per_step": e2e_blob_bytes + 8 * (B + 1),
+                      "d2h_bytes_per_step": int(h_dec.numel()), "images_equal_device_decode_sample": bool(torch.equal(h_dec[:8], ref_dec)),
+                      "call": "lrfb_qmf_decode_bytes_host (C ABI): encoded images in host memory -> uint8 images in pinned host memory "
+                              "(device un-framing + inflate + decode, chunked copy-back); bound by the D2H copy of the images"}
+        del h_dec
     lib.lrfb_ctx_destroy(ctx)
 
     # ---- plain concurrent H2D copy of the same bytes: the machine's ceiling for `e2e` (PCIe / host memory) ----------
@@ -617,6 +638,7 @@ def main():
                                     "what": "the same pinned input copied to the device by plain concurrent "
                                             "cudaMemcpyAsync on every rank, nothing else running",
                                     "frac_of_ceiling": e2e_bytes_value / e2e_ceiling}},
+            "decode_e2e": decode_e2e,
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
             "roofline": roofline,
