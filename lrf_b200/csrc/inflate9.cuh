@@ -9,8 +9,8 @@
 // (per-length code counts and a symbol table sorted by code): no large lookup tables, a few hundred bytes per stream.
 //
 // Mapping: one thread per image walks the framing (nested big-endian length prefixes) and notes where each column's
-// stream starts; then one warp per column: all lanes stage the stream in shared memory, lane 0 decodes it into a shared
-// output buffer (match copies included), all lanes verify the adler32 and copy the column into the record.
+// stream starts; then one warp per column: lane 0 decodes the stream into a shared output buffer (match copies included),
+// all lanes verify the adler32 and copy the column into the record.
 #pragma once
 #include "lrfb_common.cuh"
 
@@ -33,7 +33,7 @@ struct Params {
   int max_len;                 // longest column (sizes the shared buffers)
 };
 
-__host__ __device__ inline int smem_bytes(int max_len) { return 2 * ((max_len + 64 + 15) & ~15) + 1024; }
+__host__ __device__ inline int smem_bytes(int max_len) { return ((max_len + 64 + 15) & ~15) + 1024; }
 
 __device__ inline unsigned be32(const unsigned char* p) {
   return ((unsigned)p[0] << 24) | ((unsigned)p[1] << 16) | ((unsigned)p[2] << 8) | (unsigned)p[3];
@@ -265,9 +265,8 @@ __global__ void __launch_bounds__(32) inflate_kernel(Params P) {
   LRFB_DYN_SMEM(smem);
   const int lane = threadIdx.x;
   const int pad = (P.max_len + 64 + 15) & ~15;
-  unsigned char* in = smem;
-  unsigned char* out = smem + pad;
-  unsigned char* scratch = smem + 2 * pad;
+  unsigned char* out = smem;
+  unsigned char* scratch = smem + pad;
   const long long total = (long long)P.batch * P.cols_total;
   for (long long s = blockIdx.x; s < total; s += gridDim.x) {
     if (*reinterpret_cast<volatile int*>(P.error)) break;
@@ -276,13 +275,8 @@ __global__ void __launch_bounds__(32) inflate_kernel(Params P) {
     while (mtx + 1 < P.n_mat && c >= P.col0[mtx] + P.ncols[mtx]) ++mtx;
     const int want = P.len[mtx], r = c - P.col0[mtx];
     const int n = (int)P.col_len[(long long)img * P.cols_total + c];
-    const unsigned char* src = P.blob + P.offsets[img] + P.col_pos[(long long)img * P.cols_total + c];
-    if (n > pad - 16) {
-      if (lane == 0) flag_error(P, img);
-      continue;
-    }
-    for (int i = lane; i < n + 16; i += 32) in[i] = i < n ? src[i] : (unsigned char)0;
-    __syncwarp();
+    // the stream (about a sixth of the column) is read where it lies: lane 0's byte loads hit L1 after the first touch of a line
+    const unsigned char* in = P.blob + P.offsets[img] + P.col_pos[(long long)img * P.cols_total + c];
     int ok = 0, tpos = 0;
     if (lane == 0) ok = inflate_stream(in, n, out, want, scratch, tpos) ? 1 : 0;
     ok = __shfl_sync(0xffffffffu, ok, 0);
