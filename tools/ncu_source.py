@@ -13,6 +13,8 @@ out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_ou
 rows = list(csv.reader(out.splitlines()))
 hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr, data = rows[hdr_i], rows[hdr_i + 1:]
+end = next((i for i, r in enumerate(data) if len(r) < len(hdr)), len(data))  # a report with several launches: the first
+data = data[:end]
 ix = {h: i for i, h in enumerate(hdr)}
 S = ix["# Samples"]
 tot = sum(int(r[S] or 0) for r in data)
