@@ -146,12 +146,14 @@ def test_device_packer_refuses_columns_beyond_the_window():
 
 
 @pytest.mark.gpu
-def test_encode_bytes_host_pipeline_ragged_chunks():
-    """lrfb_qmf_encode_bytes_host (pinned host images -> finished streams) over 5 chunks with a ragged tail equals
-    encode + Python packer per image; the public batch API takes the same route for pinned inputs."""
+@pytest.mark.parametrize("B,chunk_images", [(37, 2), (150, 20), (5, 25)])
+def test_encode_bytes_host_pipeline_ragged_chunks(B, chunk_images):
+    """lrfb_qmf_encode_bytes_host (pinned host images -> finished streams) over uneven chunks equals encode + Python
+    packer per image; the public batch API takes the same route for pinned inputs.  The pipeline chunk is 4 x
+    chunk_images: 37 images = 4 x 8 + 5, 150 = 80 + 70, 5 = one chunk."""
     from oracle import qmf_port as port
 
-    H, W, B = 96, 160, 37
+    H, W = 96, 160
     pool = torch.stack([port.s_nat(2000 + i, H, W) for i in range(5)])
     imgs = pool[torch.arange(B) % 5].contiguous().pin_memory()
     records, lay, meta = compression.qmf_encode_batch(imgs.cuda(), quality=12, return_records=True)
@@ -162,7 +164,7 @@ def test_encode_bytes_host_pipeline_ragged_chunks():
     ctx = C.c_void_p()
     _cabi.check(lib.lrfb_ctx_create(0, C.byref(ctx)), "ctx")
     try:
-        _cabi.check(lib.lrfb_ctx_set_chunk_bytes(ctx, 2 * 3 * H * W), "chunk")  # 4 x 2 = 8 images per chunk: 4 full + 5
+        _cabi.check(lib.lrfb_ctx_set_chunk_bytes(ctx, chunk_images * 3 * H * W), "chunk")
         mj = packing.dict_to_bytes(meta)
         cap = B * int(lib.lrfb_qmf_pack_bound(C.byref(cfg), len(mj)))
         blob = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
