@@ -1755,9 +1755,20 @@ LRFB_EXPORT int64_t lrfb_qmf_unpack_device_workspace(const lrfb_qmf_config* cfg,
   return 256 + 8ll * batch * cols_total;
 }
 
+namespace {
+int unpack_device_impl(const lrfb_qmf_config* cfg, int32_t batch, const uint8_t* d_blob, const int64_t* d_offsets,
+                       int8_t* d_records, void* d_workspace, int64_t workspace_bytes, void* stream, int image_base);
+}
 LRFB_EXPORT int32_t lrfb_qmf_unpack_device(const lrfb_qmf_config* cfg, int32_t batch, const uint8_t* d_blob,
                                            const int64_t* d_offsets, int8_t* d_records, void* d_workspace,
                                            int64_t workspace_bytes, void* stream) {
+  return unpack_device_impl(cfg, batch, d_blob, d_offsets, d_records, d_workspace, workspace_bytes, stream, 0);
+}
+namespace {
+// `d_offsets` may point into a longer table (offsets are absolute positions in d_blob); `image_base` is the index of its
+// first image in the caller's batch, for the error message
+int unpack_device_impl(const lrfb_qmf_config* cfg, int32_t batch, const uint8_t* d_blob, const int64_t* d_offsets,
+                       int8_t* d_records, void* d_workspace, int64_t workspace_bytes, void* stream, int image_base) {
   if (!d_blob || !d_offsets || !d_records || !d_workspace || batch <= 0) return fail(LRFB_E_ARG, "bad arguments");
   lrfb_qmf_layout L;
   int rc = lrfb_qmf_layout_query(cfg, &L);
@@ -1804,9 +1815,11 @@ LRFB_EXPORT int32_t lrfb_qmf_unpack_device(const lrfb_qmf_config* cfg, int32_t b
 #else
   err = *P.error;
 #endif
-  if (err) return fail(LRFB_E_ARG, "encoded image %d is malformed (framing, deflate stream, length or adler32)", err - 1);
+  if (err)
+    return fail(LRFB_E_ARG, "encoded image %d is malformed (framing, deflate stream, length or adler32)", image_base + err - 1);
   return 0;
 }
+}  // namespace
 
 // Encoded images in host memory -> uint8 images in host memory, the whole of lrf.qmf_decode for a batch: the streams go up
 // once (a few KB per image), are un-framed and inflated on the device, and the decode kernel's output comes back chunk by
@@ -1833,14 +1846,21 @@ LRFB_EXPORT int32_t lrfb_qmf_decode_bytes_host(lrfb_ctx* c, const lrfb_qmf_confi
   if ((rc = grow(&c->d_pws, &c->pws_cap, (size_t)uws))) return rc;
   if ((rc = h2d(c->d_blob, h_blob, (size_t)total, c->stream))) return rc;
   if ((rc = h2d(c->d_offs, h_offsets, (size_t)(batch + 1) * 8, c->stream))) return rc;
-  if ((rc = lrfb_qmf_unpack_device(cfg, batch, reinterpret_cast<const uint8_t*>(c->d_blob), reinterpret_cast<const int64_t*>(c->d_offs),
-                                   reinterpret_cast<int8_t*>(c->d_in), c->d_pws, (int64_t)c->pws_cap, (void*)(uintptr_t)c->stream)))
-    return rc;
   int idx = 0;
   for (int i0 = 0; i0 < batch; i0 += chunk, ++idx) {
     const int n = std::min(chunk, batch - i0);
     const int oslot = idx & 1;
     uint8_t* d_img = reinterpret_cast<uint8_t*>(c->d_out) + (size_t)oslot * chunk * img_bytes;
+    // un-framing + inflate chunk by chunk (the copy-back of the previous chunks runs meanwhile): done for the whole batch
+    // up front it is 11 ms of a 4096-image call during which the copy engine, the bound of this call, has nothing to do
+    if ((rc = unpack_device_impl(cfg, n, reinterpret_cast<const uint8_t*>(c->d_blob), reinterpret_cast<const int64_t*>(c->d_offs) + i0,
+                                 reinterpret_cast<int8_t*>(c->d_in) + (size_t)i0 * L.record_bytes, c->d_pws, (int64_t)c->pws_cap,
+                                 (void*)(uintptr_t)c->stream, i0))) {
+#ifndef LRFB_SIM
+      sync_stream(c->back);  // earlier chunks may still be on their way into h_images
+#endif
+      return rc;
+    }
 #ifndef LRFB_SIM
     if (idx >= 2) cudaStreamWaitEvent(c->stream, c->drained[oslot], 0);
 #endif

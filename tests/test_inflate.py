@@ -100,5 +100,15 @@ def test_decode_bytes_host_matches_decode_batch():
         rc = lib.lrfb_qmf_decode_bytes_host(ctx, C.byref(cfg), B, blob.ctypes.data_as(C.c_void_p),
                                             offs.ctypes.data_as(C.c_void_p), C.c_void_p(out.data_ptr()))
         assert rc != 0 and b"image 3" in lib.lrfb_last_error()
+        blob[int(offs[4]) - 9] ^= 0x10
+        blob[int(offs[21]) - 9] ^= 0x10  # image 20 sits in the third chunk: the index reported is the batch's, not the chunk's
+        rc = lib.lrfb_qmf_decode_bytes_host(ctx, C.byref(cfg), B, blob.ctypes.data_as(C.c_void_p),
+                                            offs.ctypes.data_as(C.c_void_p), C.c_void_p(out.data_ptr()))
+        assert rc != 0 and b"image 20" in lib.lrfb_last_error()
+        blob[int(offs[21]) - 9] ^= 0x10
+        out.zero_()
+        _cabi.check(lib.lrfb_qmf_decode_bytes_host(ctx, C.byref(cfg), B, blob.ctypes.data_as(C.c_void_p),
+                                                   offs.ctypes.data_as(C.c_void_p), C.c_void_p(out.data_ptr())), "after errors")
+        assert torch.equal(out, want)
     finally:
         lib.lrfb_ctx_destroy(ctx)
