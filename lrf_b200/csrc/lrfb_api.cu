@@ -1306,12 +1306,15 @@ LRFB_EXPORT int32_t lrfb_qmf_decode_host(lrfb_ctx* c, const lrfb_qmf_config* cfg
   // d_in doubles as the record buffer (whole batch: records are ~40x smaller than images), d_out holds two image chunks
   if ((rc = grow(&c->d_in, &c->in_cap, (size_t)batch * L.record_bytes))) return rc;
   if ((rc = grow(&c->d_out, &c->out_cap, (size_t)2 * chunk * img_bytes))) return rc;
-  if ((rc = h2d(c->d_in, h_factors, (size_t)batch * L.record_bytes, c->stream))) return rc;
   int idx = 0;
   for (int i0 = 0; i0 < batch; i0 += chunk, ++idx) {
     const int n = std::min(chunk, batch - i0);
     const int oslot = idx & 1;
     uint8_t* d_img = reinterpret_cast<uint8_t*>(c->d_out) + (size_t)oslot * chunk * img_bytes;
+    // the records go up chunk by chunk too: the copy-back, the bound of this call, starts after one chunk's worth
+    if ((rc = h2d(reinterpret_cast<int8_t*>(c->d_in) + (size_t)i0 * L.record_bytes, h_factors + (size_t)i0 * L.record_bytes,
+                  (size_t)n * L.record_bytes, c->stream)))
+      return rc;
 #ifndef LRFB_SIM
     if (idx >= 2) cudaStreamWaitEvent(c->stream, c->drained[oslot], 0);
 #endif
